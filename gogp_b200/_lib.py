@@ -1,0 +1,102 @@
+"""ctypes binding of the C-ABI (include/gogp_b200.h).
+
+This is the Python counterpart of the cgo stub in INTEGRATION.md: the same
+entry points, the same plain pointers and sizes.  There is no fallback: if the
+shared library is missing the import fails, and if no CUDA device is present
+``gogp_create`` reports GOGP_CUDA_ERROR.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgogp_b200.so")
+
+# gogp_status
+OK, BAD_ARGUMENT, NOT_POSITIVE_DEFINITE, ILL_CONDITIONED, CUDA_ERROR, NCCL_ERROR, OUT_OF_MEMORY, NOT_READY, \
+    UNSUPPORTED = range(9)
+
+# gogp_op_kind
+OP_CONST, OP_PARAM, OP_ADD, OP_MUL, OP_NORMAL, OP_PERIODIC, OP_MATERN32, OP_MATERN52, OP_MATERN52_TEXTBOOK = range(9)
+
+PHASES = ("upload", "build", "potrf", "solve", "potri", "trace", "predict")
+
+# every symbol include/gogp_b200.h declares
+SYMBOLS = (
+    "gogp_create", "gogp_destroy", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_lml",
+    "gogp_produce", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
+    "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
+    "gogp_debug_gemm",
+)
+
+
+class Op(C.Structure):
+    """gogp_op"""
+    _fields_ = [
+        ("kind", C.c_uint8),
+        ("dim", C.c_uint8),
+        ("param", C.c_int16 * 2),
+        ("scale", C.c_double * 2),
+        ("constant", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "gogp_b200: %s is missing -- build the CUDA extension first "
+            "(python -m gogp_b200.build); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    dp = C.POINTER(C.c_double)
+    H = C.c_void_p
+    L.gogp_create.argtypes = [C.c_int, C.POINTER(Op), C.c_int, C.c_int, C.POINTER(Op), C.c_int, C.c_int, C.c_int,
+                              C.POINTER(H)]
+    L.gogp_create.restype = C.c_int
+    L.gogp_destroy.argtypes = [H]
+    L.gogp_destroy.restype = None
+    L.gogp_set_data.argtypes = [H, dp, dp, C.c_int64]
+    L.gogp_set_data.restype = C.c_int
+    L.gogp_observe.argtypes = [H, dp, C.c_int, dp, dp, C.c_int64, dp]
+    L.gogp_observe.restype = C.c_int
+    L.gogp_gradient.argtypes = [H, dp, C.c_int64]
+    L.gogp_gradient.restype = C.c_int
+    L.gogp_absorb.argtypes = [H, dp, dp, dp, dp, C.c_int64]
+    L.gogp_absorb.restype = C.c_int
+    L.gogp_lml.argtypes = [H, dp]
+    L.gogp_lml.restype = C.c_int
+    L.gogp_produce.argtypes = [H, dp, C.c_int64, dp, dp]
+    L.gogp_produce.restype = C.c_int
+    L.gogp_get_alpha.argtypes = [H, dp, C.c_int64]
+    L.gogp_get_alpha.restype = C.c_int
+    L.gogp_get_factor.argtypes = [H, dp, C.c_int64]
+    L.gogp_get_factor.restype = C.c_int
+    L.gogp_last_error.argtypes = [H]
+    L.gogp_last_error.restype = C.c_char_p
+    L.gogp_status_string.argtypes = [C.c_int]
+    L.gogp_status_string.restype = C.c_char_p
+    L.gogp_phase_times.argtypes = [H, dp]
+    L.gogp_phase_times.restype = C.c_int
+    L.gogp_launch_count.argtypes = [H]
+    L.gogp_launch_count.restype = C.c_int64
+    L.gogp_debug_fetch.argtypes = [H, C.c_int, dp, C.c_int64]
+    L.gogp_debug_fetch.restype = C.c_int
+    L.gogp_debug_build.argtypes = [H, dp, dp, dp, C.c_int64, dp]
+    L.gogp_debug_build.restype = C.c_int
+    L.gogp_debug_fp64_peak.argtypes = [H, C.c_int, dp]
+    L.gogp_debug_fp64_peak.restype = C.c_int
+    L.gogp_debug_gemm.argtypes = [H, C.c_int64, C.c_int64, C.c_int, C.c_int, dp]
+    L.gogp_debug_gemm.restype = C.c_int
+    _lib = L
+    return L
+
+
+def dptr(a):
+    """float64 C-contiguous numpy array (or None) -> double*"""
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(C.c_double))

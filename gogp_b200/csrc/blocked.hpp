@@ -1,0 +1,82 @@
+// Recursive blocked dense algebra over 128x128 tiles, written against a small
+// backend of tile primitives so the same recursion drives the CUDA kernels (the
+// product) and, in tests/cpu_blocked_test.cc only, a naive host backend that
+// checks the index arithmetic without a GPU.
+//
+// Storage: row-major, lower triangle, leading dimension ld; everything is a
+// multiple of 128.  All O(n^3) work is expressed as  C = beta C + alpha A B^T
+// ("NT" GEMM, k contiguous in both operands):
+//   potrf(A)       A = L L^T             n^3/3   (reference: gp.L.Factorize, gp/gp.go:228)
+//   trsm(B, L)     X L^T = B             m n^2   (Produce's L.SolveTo, gp/gp.go:337-340)
+//   trtri_t(L)     U = L^-T (upper)      n^3/3   \  together K^-1, replacing the per-parameter
+//   lauum(U)       K^-1 = U U^T (lower)  n^3/3   /  L.SolveTo of gp/gp.go:454,480
+// The 128x128 diagonal blocks are factored by a leaf kernel that also returns
+// their inverses, so every triangular solve with a diagonal block is a GEMM.
+#pragma once
+#include <stdint.h>
+
+namespace gogp {
+
+constexpr int64_t kTile = 128;
+
+enum : int { BL_FULL = 0, BL_LOWER = 1, BL_KTRI = 2, BL_DIAG_OUT = 4 };  // == GemmMode
+
+template <class BE>
+struct Blocked {
+    BE& be;
+    double* A;     // Npad x Npad: K -> L
+    int64_t ld;
+    double* winv;  // [T][128][128] inverses of L's diagonal tiles
+
+    static int64_t split(int64_t n) { return (n / kTile / 2) * kTile; }
+    double* at(double* M, int64_t r, int64_t c) const { return M + r * ld + c; }
+
+    // A[o:o+n, o:o+n] = L L^T
+    void potrf(int64_t o, int64_t n) {
+        if (n == kTile) {
+            be.potrf_leaf(at(A, o, o), ld, winv + (o / kTile) * kTile * kTile, (int)o);
+            return;
+        }
+        const int64_t n1 = split(n), n2 = n - n1;
+        potrf(o, n1);
+        trsm(at(A, o + n1, o), ld, n2, o, n1);
+        be.gemm(at(A, o + n1, o + n1), ld, at(A, o + n1, o), ld, at(A, o + n1, o), ld, n2, n2, n1, -1.0, 1.0, BL_LOWER,
+                nullptr);
+        potrf(o + n1, n2);
+    }
+
+    // B (m x n, ldb) <- B L^-T with L = A[o:o+n, o:o+n]
+    void trsm(double* B, int64_t ldb, int64_t m, int64_t o, int64_t n) {
+        if (n == kTile) {
+            // X = B Winv^T, in place: one CTA owns a full 128-row block of B (n == BN)
+            be.gemm(B, ldb, B, ldb, winv + (o / kTile) * kTile * kTile, kTile, m, kTile, kTile, 1.0, 0.0, BL_FULL,
+                    nullptr);
+            return;
+        }
+        const int64_t n1 = split(n), n2 = n - n1;
+        trsm(B, ldb, m, o, n1);
+        be.gemm(B + n1, ldb, B, ldb, at(A, o + n1, o), ld, m, n2, n1, -1.0, 1.0, BL_FULL, nullptr);
+        trsm(B + n1, ldb, m, o + n1, n2);
+    }
+
+    // U[o:o+n, o:o+n] (upper, in Bm with the same ld) = L[o:o+n, o:o+n]^-T
+    void trtri_t(double* Bm, int64_t o, int64_t n) {
+        if (n == kTile) {
+            be.trtri_leaf(winv + (o / kTile) * kTile * kTile, at(Bm, o, o), ld);
+            return;
+        }
+        const int64_t n1 = split(n), n2 = n - n1;
+        trtri_t(Bm, o, n1);
+        trtri_t(Bm, o + n1, n2);
+        // U12 = -U11 L21^T (U11 upper triangular: k >= row), then U12 <- U12 L22^-T
+        be.gemm(at(Bm, o, o + n1), ld, at(Bm, o, o), ld, at(A, o + n1, o), ld, n1, n2, n1, -1.0, 0.0, BL_KTRI, nullptr);
+        trsm(at(Bm, o, o + n1), ld, n1, o + n1, n2);
+    }
+
+    // K^-1 = U U^T: strictly-lower tiles into Bm's lower triangle, diagonal tiles into dg
+    void lauum(double* Bm, double* dg, int64_t n) {
+        be.gemm(Bm, ld, Bm, ld, Bm, ld, n, n, n, 1.0, 0.0, BL_LOWER | BL_KTRI | BL_DIAG_OUT, dg);
+    }
+};
+
+}  // namespace gogp

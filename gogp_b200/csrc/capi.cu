@@ -1,0 +1,621 @@
+// C-ABI of the B200 GP hot path (include/gogp_b200.h): handle, memory, and the
+// sequencing of the sm_100a kernels behind gp.GP.Observe / Gradient / Absorb /
+// LML / Produce (reference gp/gp.go).  No CPU fallback: every numerical step is
+// a kernel launch on the handle's stream.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gogp_b200.h"
+#include "blocked.hpp"
+#include "kernels.h"
+#include "program.h"
+
+using namespace gogp;
+
+namespace {
+
+constexpr double kNoNoise = 1e-5;  // gp/gp.go:43
+constexpr int64_t kProduceChunk = 8192;
+
+inline int64_t pad_tile(int64_t n) { return n <= 0 ? 0 : ((n + TILE - 1) / TILE) * TILE; }
+
+struct CudaBackend {
+    cudaStream_t s;
+    int* info;
+    int64_t* launches;
+    void gemm(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m, int64_t n,
+              int64_t k, double alpha, double beta, int mode, double* cdiag) {
+        launch_dgemm_nt(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s);
+        ++*launches;
+    }
+    void potrf_leaf(double* A, int64_t ld, double* winv, int base) {
+        launch_potrf_leaf(A, ld, winv, info, base, s);
+        ++*launches;
+    }
+    void trtri_leaf(const double* winv, double* dst, int64_t ld) {
+        launch_trtri_leaf(winv, dst, ld, s);
+        ++*launches;
+    }
+};
+
+}  // namespace
+
+struct gogp_handle {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    int ndim = 1;
+    Program simil, noise;
+    int nts = 0, ntn = 0;
+    std::vector<double> theta_s, theta_n;  // natural scale
+    double noise_var = 0.0;
+    std::vector<double> noise_dlog;
+
+    int64_t N = 0, Npad = 0;   // current data
+    int64_t cap = 0;           // allocated padded size
+    int64_t cap_grad = 0;      // padded size the gradient buffers are allocated for
+    double *dXraw = nullptr, *dXt = nullptr, *dY = nullptr;
+    double *dA = nullptr, *dWinv = nullptr;
+    double *dB = nullptr, *dDg = nullptr, *dPartial = nullptr;
+    double *dAlpha = nullptr, *dW = nullptr, *dZ = nullptr, *dRed = nullptr, *dGx = nullptr;
+    int* dInfo = nullptr;
+    double* hPin = nullptr;  // pinned staging for small results
+    int64_t hPinCap = 0;
+    // Produce scratch
+    double *dZraw = nullptr, *dZt = nullptr, *dBt = nullptr, *dPv = nullptr;
+    int64_t capM = 0, capBt = 0;
+
+    bool has_data = false, factored = false, have_kinv = false, with_obs = false;
+    double lml = 0.0;
+    std::string err;
+    double phase_ms[GOGP_NPHASE] = {0};
+    cudaEvent_t ev[8] = {nullptr};
+    int64_t launches = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+            return e_ == cudaErrorMemoryAllocation ? GOGP_OUT_OF_MEMORY : GOGP_CUDA_ERROR; \
+        }                                                                                  \
+    } while (0)
+
+gogp_status fail(gogp_handle* h, gogp_status s, const std::string& msg) {
+    h->err = msg;
+    return s;
+}
+
+void free_dev(double*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+gogp_status ensure_pin(gogp_handle* h, int64_t n) {
+    if (n <= h->hPinCap) return GOGP_OK;
+    if (h->hPin) cudaFreeHost(h->hPin);
+    h->hPin = nullptr;
+    h->hPinCap = 0;
+    CK(cudaMallocHost(&h->hPin, (size_t)n * sizeof(double)));
+    h->hPinCap = n;
+    return GOGP_OK;
+}
+
+gogp_status ensure_capacity(gogp_handle* h, int64_t Npad) {
+    if (Npad <= h->cap) return GOGP_OK;
+    free_dev(h->dXraw); free_dev(h->dXt); free_dev(h->dY); free_dev(h->dA); free_dev(h->dWinv);
+    free_dev(h->dAlpha); free_dev(h->dW); free_dev(h->dZ); free_dev(h->dGx);
+    free_dev(h->dB); free_dev(h->dDg); free_dev(h->dPartial);
+    h->cap = 0;
+    h->cap_grad = 0;
+    const size_t v = (size_t)Npad * sizeof(double);
+    CK(cudaMalloc(&h->dXraw, v * h->ndim));
+    CK(cudaMalloc(&h->dXt, v * h->ndim));
+    CK(cudaMalloc(&h->dY, v));
+    CK(cudaMalloc(&h->dA, v * Npad));
+    CK(cudaMalloc(&h->dWinv, v * TILE));
+    CK(cudaMalloc(&h->dAlpha, v));
+    CK(cudaMalloc(&h->dW, v));
+    CK(cudaMalloc(&h->dZ, v));
+    CK(cudaMalloc(&h->dGx, v * h->ndim));
+    h->cap = Npad;
+    return GOGP_OK;
+}
+
+gogp_status ensure_grad_capacity(gogp_handle* h) {
+    if (h->cap_grad >= h->cap && h->dB) return GOGP_OK;
+    free_dev(h->dB); free_dev(h->dDg); free_dev(h->dPartial);
+    const int64_t Npad = h->cap;
+    const int64_t T = Npad / TILE;
+    CK(cudaMalloc(&h->dB, (size_t)Npad * Npad * sizeof(double)));
+    CK(cudaMalloc(&h->dDg, (size_t)Npad * TILE * sizeof(double)));
+    CK(cudaMalloc(&h->dPartial, (size_t)(T * (T + 1) / 2) * (kMaxTheta + 1) * sizeof(double)));
+    h->cap_grad = Npad;
+    return GOGP_OK;
+}
+
+// Upload X (N x D) and Y (N); build the dimension-major copy.
+gogp_status upload_data(gogp_handle* h, const double* X, const double* Y, int64_t N) {
+    if (N < 0) return fail(h, GOGP_BAD_ARGUMENT, "negative N");
+    const int64_t Npad = pad_tile(N);
+    h->N = N;
+    h->Npad = Npad;
+    h->has_data = true;
+    h->factored = false;
+    h->have_kinv = false;
+    if (N == 0) return GOGP_OK;
+    if (!X || !Y) return fail(h, GOGP_BAD_ARGUMENT, "X and Y must be given when N > 0");
+    gogp_status st = ensure_capacity(h, Npad);
+    if (st != GOGP_OK) return st;
+    CK(cudaMemcpyAsync(h->dXraw, X, (size_t)N * h->ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->dY, 0, (size_t)Npad * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(h->dY, Y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_transpose_x(h->dXraw, h->dXt, N, Npad, h->ndim, h->stream);
+    ++h->launches;
+    // pageable host memory: the copies above are staged synchronously by the
+    // runtime, so the caller's buffers are free on return (cgo pointer rules)
+    return GOGP_OK;
+}
+
+void set_theta(gogp_handle* h, const double* ts, const double* tn) {
+    for (int i = 0; i < h->nts; ++i) h->theta_s[i] = ts[i];
+    for (int i = 0; i < h->ntn; ++i) h->theta_n[i] = tn[i];
+    h->noise_dlog.assign(h->ntn > 0 ? h->ntn : 1, 0.0);
+    h->noise_var = h->noise.eval_scalar(h->theta_n.data(), h->noise_dlog.data());
+}
+
+// absorb (gp/gp.go:89-239): build K, factor, alpha; then LML (gp/gp.go:244-253).
+gogp_status absorb(gogp_handle* h) {
+    h->factored = false;
+    h->have_kinv = false;
+    for (double& m : h->phase_ms) m = 0.0;
+    if (!h->has_data) return fail(h, GOGP_NOT_READY, "no observations: call gogp_set_data or pass X, Y");
+    if (h->N == 0) {
+        h->lml = 0.0;
+        h->factored = true;
+        return GOGP_OK;
+    }
+    const int64_t N = h->N, Npad = h->Npad;
+    cudaStream_t s = h->stream;
+    DevProgram prog;
+    h->simil.bind(h->theta_s.data(), &prog);
+
+    CK(cudaMemsetAsync(h->dInfo, 0, sizeof(int), s));
+    CK(cudaEventRecord(h->ev[0], s));
+    launch_cov_build(prog, h->dXt, N, Npad, h->ndim, h->noise_var, h->dA, s);
+    ++h->launches;
+    CK(cudaEventRecord(h->ev[1], s));
+
+    CudaBackend be{s, h->dInfo, &h->launches};
+    Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
+    bl.potrf(0, Npad);
+    CK(cudaEventRecord(h->ev[2], s));
+
+    // alpha = L^-T (L^-1 y)
+    CK(cudaMemcpyAsync(h->dW, h->dY, (size_t)Npad * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    launch_trsv_lower(h->dA, Npad, h->dWinv, h->dW, h->dZ, Npad, false, s, &h->launches);
+    launch_trsv_lower(h->dA, Npad, h->dWinv, h->dZ, h->dAlpha, Npad, true, s, &h->launches);
+    launch_logdet_dot(h->dA, Npad, h->dY, h->dAlpha, N, h->dRed, s);
+    ++h->launches;
+    CK(cudaEventRecord(h->ev[3], s));
+    gogp_status st = ensure_pin(h, 8);
+    if (st != GOGP_OK) return st;
+    CK(cudaMemcpyAsync(h->hPin, h->dRed, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->hPin + 2, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->phase_ms[GOGP_PHASE_BUILD] = ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+    h->phase_ms[GOGP_PHASE_POTRF] = ms;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    h->phase_ms[GOGP_PHASE_SOLVE] = ms;
+
+    int info = 0;
+    memcpy(&info, h->hPin + 2, sizeof(int));
+    if (info != 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "Factorize: covariance matrix is not positive definite (pivot %d of %lld)", info,
+                 (long long)N);
+        return fail(h, GOGP_NOT_POSITIVE_DEFINITE, buf);
+    }
+    const double sumlog = h->hPin[0], ydot = h->hPin[1];
+    h->lml = -0.5 * (double)N * std::log(2 * M_PI) - 0.5 * (2.0 * sumlog) - 0.5 * ydot;
+    h->factored = true;
+    return GOGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+gogp_status gogp_create(int ndim, const gogp_op* simil, int n_simil_ops, int ntheta_simil, const gogp_op* noise,
+                        int n_noise_ops, int ntheta_noise, int device, gogp_handle** out) {
+    if (!out) return GOGP_BAD_ARGUMENT;
+    *out = nullptr;
+    gogp_handle* h = new gogp_handle();
+    *out = h;  // returned even on failure so gogp_last_error can be read; caller destroys it
+    h->dev = device;
+    h->ndim = ndim;
+    if (ndim < 1 || ndim > 64) return fail(h, GOGP_BAD_ARGUMENT, "ndim must be in [1, 64]");
+    if (!simil || n_simil_ops <= 0) return fail(h, GOGP_BAD_ARGUMENT, "a similarity kernel descriptor is required");
+    std::string err;
+    if (!h->simil.lower(simil, n_simil_ops, ntheta_simil, ndim, true, &err)) return fail(h, GOGP_UNSUPPORTED, err);
+    if (noise && n_noise_ops > 0) {
+        if (!h->noise.lower(noise, n_noise_ops, ntheta_noise, ndim, false, &err)) return fail(h, GOGP_UNSUPPORTED, err);
+    } else {
+        gogp_op def{};  // ConstantNoise(nonoise), gp/gp.go:46-48
+        def.kind = GOGP_OP_CONST;
+        def.constant = kNoNoise * kNoNoise;
+        h->noise.lower(&def, 1, 0, ndim, false, &err);
+    }
+    h->nts = ntheta_simil;
+    h->ntn = h->noise.ntheta;
+    h->theta_s.assign(h->nts > 0 ? h->nts : 1, 0.0);  // defaults(): zero parameters, gp/gp.go:50-56
+    h->theta_n.assign(h->ntn > 0 ? h->ntn : 1, 0.0);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(h, GOGP_CUDA_ERROR, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(h, GOGP_BAD_ARGUMENT, "device index out of range");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+    CK(cudaMalloc(&h->dRed, 64 * sizeof(double)));
+    CK(cudaMalloc(&h->dInfo, sizeof(int)));
+    set_theta(h, h->theta_s.data(), h->theta_n.data());
+    return GOGP_OK;
+}
+
+void gogp_destroy(gogp_handle* h) {
+    if (!h) return;
+    if (h->stream) {
+        cudaSetDevice(h->dev);
+        cudaStreamSynchronize(h->stream);
+    }
+    free_dev(h->dXraw); free_dev(h->dXt); free_dev(h->dY); free_dev(h->dA); free_dev(h->dWinv);
+    free_dev(h->dAlpha); free_dev(h->dW); free_dev(h->dZ); free_dev(h->dGx);
+    free_dev(h->dB); free_dev(h->dDg); free_dev(h->dPartial); free_dev(h->dRed);
+    free_dev(h->dZraw); free_dev(h->dZt); free_dev(h->dBt); free_dev(h->dPv);
+    if (h->dInfo) cudaFree(h->dInfo);
+    if (h->hPin) cudaFreeHost(h->hPin);
+    for (auto& ev : h->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+gogp_status gogp_set_data(gogp_handle* h, const double* X, const double* Y, int64_t N) {
+    if (!h) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    gogp_status st = upload_data(h, X, Y, N);
+    if (st != GOGP_OK) return st;
+    CK(cudaStreamSynchronize(h->stream));
+    return GOGP_OK;
+}
+
+gogp_status gogp_observe(gogp_handle* h, const double* log_theta, int with_obs, const double* X, const double* Y,
+                         int64_t N, double* lml) {
+    if (!h || !lml) return GOGP_BAD_ARGUMENT;
+    if (!log_theta && h->nts + h->ntn > 0) return fail(h, GOGP_BAD_ARGUMENT, "log_theta is NULL");
+    CK(cudaSetDevice(h->dev));
+    std::vector<double> ts(h->nts > 0 ? h->nts : 1), tn(h->ntn > 0 ? h->ntn : 1);
+    for (int i = 0; i < h->nts; ++i) ts[i] = std::exp(log_theta[i]);  // gp/gp.go:378-381
+    for (int i = 0; i < h->ntn; ++i) tn[i] = std::exp(log_theta[h->nts + i]);
+    set_theta(h, ts.data(), tn.data());
+    if (with_obs && N > 0 && (!X || !Y)) return fail(h, GOGP_BAD_ARGUMENT, "with_obs needs X and Y");
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    if (with_obs || X) {
+        gogp_status st = upload_data(h, X, Y, N);
+        if (st != GOGP_OK) return st;
+    }
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    h->with_obs = with_obs != 0;
+    gogp_status st = absorb(h);
+    if (st != GOGP_OK) return st;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+    h->phase_ms[GOGP_PHASE_UPLOAD] = ms;
+    *lml = h->lml;
+    return GOGP_OK;
+}
+
+gogp_status gogp_absorb(gogp_handle* h, const double* theta_simil, const double* theta_noise, const double* X,
+                        const double* Y, int64_t N) {
+    if (!h) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    std::vector<double> ts(h->nts > 0 ? h->nts : 1, 0.0), tn(h->ntn > 0 ? h->ntn : 1, 0.0);
+    if (theta_simil)
+        for (int i = 0; i < h->nts; ++i) ts[i] = theta_simil[i];
+    if (theta_noise)
+        for (int i = 0; i < h->ntn; ++i) tn[i] = theta_noise[i];
+    set_theta(h, ts.data(), tn.data());
+    gogp_status st = upload_data(h, X, Y, N);
+    if (st != GOGP_OK) return st;
+    h->with_obs = false;
+    return absorb(h);
+}
+
+gogp_status gogp_lml(gogp_handle* h, double* lml) {
+    if (!h || !lml) return GOGP_BAD_ARGUMENT;
+    if (!h->factored) return fail(h, GOGP_NOT_READY, "LML before Observe/Absorb");
+    *lml = h->lml;
+    return GOGP_OK;
+}
+
+gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
+    if (!h || (!grad && len > 0)) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    if (!h->factored) return fail(h, GOGP_NOT_READY, "Gradient before Observe");
+    const int P = h->nts + h->ntn;
+    const int64_t N = h->N, Npad = h->Npad;
+    const int D = h->ndim;
+    const int64_t want = h->with_obs ? P + N * (D + 1) : P;
+    if (len != want) return fail(h, GOGP_BAD_ARGUMENT, "gradient length does not match the last Observe");
+    for (int64_t i = 0; i < len; ++i) grad[i] = 0.0;
+    if (N == 0) return GOGP_OK;  // gp/gp.go:427-430
+    cudaStream_t s = h->stream;
+    gogp_status st = ensure_grad_capacity(h);
+    if (st != GOGP_OK) return st;
+    DevProgram prog;
+    h->simil.bind(h->theta_s.data(), &prog);
+
+    CK(cudaEventRecord(h->ev[0], s));
+    if (!h->have_kinv) {
+        CudaBackend be{s, h->dInfo, &h->launches};
+        Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
+        bl.trtri_t(h->dB, 0, Npad);
+        bl.lauum(h->dB, h->dDg, Npad);
+        h->have_kinv = true;
+    }
+    CK(cudaEventRecord(h->ev[1], s));
+    launch_grad_trace(prog, h->dXt, h->dAlpha, h->dB, h->dDg, N, Npad, D, h->dPartial, h->dRed, s);
+    h->launches += 2;
+    if (h->with_obs) {
+        launch_grad_inputs(prog, h->dXt, h->dAlpha, h->dB, h->dDg, N, Npad, D, h->dGx, s);
+        ++h->launches;
+    }
+    CK(cudaEventRecord(h->ev[2], s));
+    const int64_t npin = (h->nts + 1) + (h->with_obs ? N * (D + 1) : 0);
+    st = ensure_pin(h, npin + 8);
+    if (st != GOGP_OK) return st;
+    CK(cudaMemcpyAsync(h->hPin, h->dRed, (h->nts + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (h->with_obs) {
+        CK(cudaMemcpyAsync(h->hPin + h->nts + 1, h->dGx, (size_t)N * D * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->hPin + h->nts + 1 + N * D, h->dAlpha, (size_t)N * sizeof(double),
+                           cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->phase_ms[GOGP_PHASE_POTRI] = ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+    h->phase_ms[GOGP_PHASE_TRACE] = ms;
+
+    for (int q = 0; q < h->nts; ++q) grad[q] = h->hPin[q];
+    const double trw = h->hPin[h->nts];
+    for (int q = 0; q < h->ntn; ++q) grad[h->nts + q] = 0.5 * trw * h->noise_dlog[q];
+    if (h->with_obs) {
+        const double* gx = h->hPin + h->nts + 1;
+        const double* al = gx + N * D;
+        for (int64_t i = 0; i < N * D; ++i) grad[P + i] = gx[i];
+        for (int64_t i = 0; i < N; ++i) grad[P + N * D + i] = -al[i];  // gp/gp.go:488-493
+    }
+    return GOGP_OK;
+}
+
+gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu, double* sigma) {
+    if (!h || M < 0) return GOGP_BAD_ARGUMENT;
+    if (M == 0) return GOGP_OK;
+    if (!Z || !mu || !sigma) return fail(h, GOGP_BAD_ARGUMENT, "Z, mu and sigma must be given");
+    CK(cudaSetDevice(h->dev));
+    const bool have_obs = h->has_data && h->N > 0;
+    if (have_obs && !h->factored) return fail(h, GOGP_NOT_READY, "Produce before Observe/Absorb");
+    cudaStream_t s = h->stream;
+    const int D = h->ndim;
+    const int64_t N = have_obs ? h->N : 0, Npad = have_obs ? h->Npad : 0;
+    DevProgram prog;
+    h->simil.bind(h->theta_s.data(), &prog);
+    const int64_t chunk = M < kProduceChunk ? pad_tile(M) : kProduceChunk;
+    if (chunk > h->capM) {
+        free_dev(h->dZraw); free_dev(h->dZt); free_dev(h->dPv);
+        h->capM = 0;
+        CK(cudaMalloc(&h->dZraw, (size_t)chunk * D * sizeof(double)));
+        CK(cudaMalloc(&h->dZt, (size_t)chunk * D * sizeof(double)));
+        CK(cudaMalloc(&h->dPv, (size_t)chunk * 3 * sizeof(double)));
+        h->capM = chunk;
+    }
+    if (chunk * Npad > h->capBt) {
+        free_dev(h->dBt);
+        h->capBt = 0;
+        CK(cudaMalloc(&h->dBt, (size_t)chunk * Npad * sizeof(double)));
+        h->capBt = chunk * Npad;
+    }
+    gogp_status st = ensure_pin(h, 3 * chunk + 8);
+    if (st != GOGP_OK) return st;
+    CK(cudaEventRecord(h->ev[6], s));
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+        const int64_t mc = (M - m0) < chunk ? (M - m0) : chunk;
+        const int64_t mpad = pad_tile(mc);
+        CK(cudaMemcpyAsync(h->dZraw, Z + m0 * D, (size_t)mc * D * sizeof(double), cudaMemcpyHostToDevice, s));
+        launch_transpose_x(h->dZraw, h->dZt, mc, mpad, D, s);
+        double* kss = h->dPv;
+        double* dmu = h->dPv + chunk;
+        double* dss = h->dPv + 2 * chunk;
+        launch_cov_self(prog, h->dZt, mc, mpad, D, kss, s);
+        h->launches += 2;
+        if (N > 0) {
+            launch_cov_cross(prog, h->dXt, N, Npad, h->dZt, mc, mpad, D, h->dBt, s);
+            launch_row_reduce(h->dBt, Npad, mc, Npad, h->dAlpha, dmu, s);  // mean = Kstar^T alpha, gp/gp.go:335
+            CudaBackend be{s, h->dInfo, &h->launches};
+            Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
+            bl.trsm(h->dBt, Npad, mpad, 0, Npad);                        // V^T = Kstar^T L^-T
+            launch_row_reduce(h->dBt, Npad, mc, Npad, nullptr, dss, s);  // diag(Kstar^T K^-1 Kstar)
+            h->launches += 3;
+        } else {
+            CK(cudaMemsetAsync(dmu, 0, (size_t)mc * sizeof(double), s));
+            CK(cudaMemsetAsync(dss, 0, (size_t)mc * sizeof(double), s));
+        }
+        CK(cudaMemcpyAsync(h->hPin, kss, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->hPin + chunk, dmu, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->hPin + 2 * chunk, dss, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        for (int64_t i = 0; i < mc; ++i) {
+            mu[m0 + i] = h->hPin[chunk + i];
+            double rad = h->hPin[i] - h->hPin[2 * chunk + i];
+            sigma[m0 + i] = std::sqrt(rad > 0.0 ? rad : (rad == rad ? 0.0 : rad));  // clamp; NaN stays NaN
+        }
+    }
+    CK(cudaEventRecord(h->ev[7], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
+    h->phase_ms[GOGP_PHASE_PREDICT] = ms;
+    return GOGP_OK;
+}
+
+gogp_status gogp_get_alpha(gogp_handle* h, double* alpha, int64_t N) {
+    if (!h || !alpha) return GOGP_BAD_ARGUMENT;
+    if (!h->factored || N != h->N) return fail(h, GOGP_NOT_READY, "alpha is not available for this N");
+    if (N == 0) return GOGP_OK;
+    CK(cudaSetDevice(h->dev));
+    CK(cudaMemcpyAsync(alpha, h->dAlpha, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GOGP_OK;
+}
+
+gogp_status gogp_debug_fetch(gogp_handle* h, int what, double* out, int64_t N) {
+    if (!h || !out) return GOGP_BAD_ARGUMENT;
+    if (N != h->N || N == 0) return fail(h, GOGP_BAD_ARGUMENT, "N does not match the absorbed data");
+    if (what == 2 && !h->have_kinv) return fail(h, GOGP_NOT_READY, "K^-1 exists only after Gradient");
+    CK(cudaSetDevice(h->dev));
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, (size_t)N * N * sizeof(double)));
+    if (what == 2)
+        launch_gather_sym(h->dB, h->Npad, h->dDg, N, tmp, h->stream);
+    else
+        launch_gather_sym(h->dA, h->Npad, nullptr, N, tmp, h->stream);
+    cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(h, GOGP_CUDA_ERROR, cudaGetErrorString(e));
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_get_factor(gogp_handle* h, double* L, int64_t N) {
+    if (!h || !L) return GOGP_BAD_ARGUMENT;
+    if (!h->factored) return fail(h, GOGP_NOT_READY, "factor before Observe/Absorb");
+    gogp_status st = gogp_debug_fetch(h, 1, L, N);
+    if (st != GOGP_OK) return st;
+    for (int64_t i = 0; i < N; ++i)
+        for (int64_t j = i + 1; j < N; ++j) L[i * N + j] = 0.0;
+    return GOGP_OK;
+}
+
+gogp_status gogp_debug_build(gogp_handle* h, const double* theta_simil, const double* theta_noise, const double* X,
+                             int64_t N, double* out) {
+    if (!h || !X || !out || N <= 0) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    std::vector<double> ts(h->nts > 0 ? h->nts : 1, 0.0), tn(h->ntn > 0 ? h->ntn : 1, 0.0);
+    if (theta_simil)
+        for (int i = 0; i < h->nts; ++i) ts[i] = theta_simil[i];
+    if (theta_noise)
+        for (int i = 0; i < h->ntn; ++i) tn[i] = theta_noise[i];
+    set_theta(h, ts.data(), tn.data());
+    std::vector<double> y((size_t)N, 0.0);
+    gogp_status st = upload_data(h, X, y.data(), N);
+    if (st != GOGP_OK) return st;
+    DevProgram prog;
+    h->simil.bind(h->theta_s.data(), &prog);
+    launch_cov_build(prog, h->dXt, N, h->Npad, h->ndim, h->noise_var, h->dA, h->stream);
+    ++h->launches;
+    return gogp_debug_fetch(h, 0, out, N);
+}
+
+gogp_status gogp_debug_fp64_peak(gogp_handle* h, int which, double* tflops) {
+    if (!h || !tflops) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev));
+    const int iters = 20000;
+    launch_fp64_peak(which, 1000, h->dRed + 32, h->stream);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        launch_fp64_peak(which, iters, h->dRed + 32, h->stream);
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+        double tf = fp64_peak_flops_per_launch(which, iters, nsm) / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    h->launches += 6;
+    CK(cudaGetLastError());
+    *tflops = best;
+    return GOGP_OK;
+}
+
+gogp_status gogp_debug_gemm(gogp_handle* h, int64_t n, int64_t k, int mode, int iters, double* tflops) {
+    if (!h || !tflops || n <= 0 || k <= 0 || n % TILE || k % TILE || iters <= 0) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    double *A = nullptr, *C = nullptr;
+    CK(cudaMalloc(&A, (size_t)n * k * sizeof(double)));
+    CK(cudaMalloc(&C, (size_t)n * n * sizeof(double)));
+    launch_fill_pattern(A, n * k, h->stream);
+    launch_fill_pattern(C, n * n, h->stream);
+    const int gm = mode ? GEMM_LOWER : GEMM_FULL;
+    launch_dgemm_nt(C, n, A, k, A, k, n, n, k, -1e-6, 1.0, gm, nullptr, h->stream);
+    cudaEventRecord(h->ev[0], h->stream);
+    for (int i = 0; i < iters; ++i) launch_dgemm_nt(C, n, A, k, A, k, n, n, k, -1e-6, 1.0, gm, nullptr, h->stream);
+    cudaEventRecord(h->ev[1], h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    cudaFree(A);
+    cudaFree(C);
+    h->launches += iters + 3;
+    if (e != cudaSuccess) return fail(h, GOGP_CUDA_ERROR, cudaGetErrorString(e));
+    CK(cudaGetLastError());
+    const double T = (double)(n / TILE);
+    const double tiles = mode ? T * (T + 1) / 2 : T * T;
+    const double flops = tiles * 2.0 * TILE * TILE * (double)k * iters;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return GOGP_OK;
+}
+
+const char* gogp_last_error(const gogp_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+const char* gogp_status_string(gogp_status s) {
+    switch (s) {
+        case GOGP_OK: return "ok";
+        case GOGP_BAD_ARGUMENT: return "bad argument";
+        case GOGP_NOT_POSITIVE_DEFINITE: return "covariance matrix is not positive definite";
+        case GOGP_ILL_CONDITIONED: return "covariance matrix is ill conditioned";
+        case GOGP_CUDA_ERROR: return "CUDA error";
+        case GOGP_NCCL_ERROR: return "NCCL error";
+        case GOGP_OUT_OF_MEMORY: return "out of device memory";
+        case GOGP_NOT_READY: return "not ready";
+        case GOGP_UNSUPPORTED: return "unsupported kernel expression";
+    }
+    return "unknown";
+}
+
+gogp_status gogp_phase_times(const gogp_handle* h, double* ms) {
+    if (!h || !ms) return GOGP_BAD_ARGUMENT;
+    for (int i = 0; i < GOGP_NPHASE; ++i) ms[i] = h->phase_ms[i];
+    return GOGP_OK;
+}
+
+int64_t gogp_launch_count(const gogp_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

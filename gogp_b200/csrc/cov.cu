@@ -1,0 +1,344 @@
+// Covariance-side kernels: K(X,X)+noise build, K(X,Z) cross build, prior
+// variance, the fused gradient trace and the input gradient.
+//
+// Reference semantics: gp/gp.go:109-156 (cov closure), :220-225 (K.SetSym over
+// j >= i), :270-278 and :322-332 (Produce), :434-486 (Gradient).  HBM-bound by
+// design: one FP64 store (build) or one FP64 load (trace) per matrix element;
+// the inputs are dimension-major ([D][Npad]) so a tile's coordinates are D
+// contiguous 1 KB runs, staged into shared memory by TMA bulk copies.
+#include <cstdio>
+
+#include "kernels.h"
+#include "kexpr.cuh"
+
+namespace gogp {
+
+__global__ void transpose_x_kernel(const double* __restrict__ X, double* __restrict__ Xt, int64_t N, int64_t Npad,
+                                   int D) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= Npad) return;
+    for (int d = 0; d < D; ++d) Xt[d * Npad + i] = i < N ? X[i * D + d] : 0.0;
+}
+
+void launch_transpose_x(const double* X, double* Xt, int64_t N, int64_t Npad, int D, cudaStream_t s) {
+    int threads = 256;
+    int blocks = (int)((Npad + threads - 1) / threads);
+    transpose_x_kernel<<<blocks, threads, 0, s>>>(X, Xt, N, Npad, D);
+}
+
+// Stage the coordinates of one row tile and one column tile: [D][128] each.
+__device__ __forceinline__ void stage_tiles(double* xr, double* xc, uint64_t* bar, const double* Rt, int64_t ldr,
+                                            int64_t row0, const double* Ct, int64_t ldc, int64_t col0, int D) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)(2 * D * TILE * sizeof(double)));
+        for (int d = 0; d < D; ++d) {
+            tma_load_1d(xr + d * TILE, Rt + d * ldr + row0, TILE * sizeof(double), bar);
+            tma_load_1d(xc + d * TILE, Ct + d * ldc + col0, TILE * sizeof(double), bar);
+        }
+    }
+    mbar_wait(bar, 0);
+}
+
+__device__ __forceinline__ double eval_program(const DevProgram& prog, const double* xc, int c, const double* xr,
+                                               int r) {
+    double k = 0.0;
+    for (int t = 0; t < prog.nterms; ++t) {
+        double p = prog.coef[t];
+        for (int fi = prog.fbeg[t]; fi < prog.fbeg[t + 1]; ++fi) {
+            const DevFactor& f = prog.f[fi];
+            p *= factor_value(f, xc[f.dim * TILE + c], xr[f.dim * TILE + r]);
+        }
+        k += p;
+    }
+    return k;
+}
+
+// out[row][col] = k(xa = C[col], xb = R[row]).  SYM: lower tiles of a square
+// matrix, + noise on the diagonal, identity in the padding; otherwise a full
+// rectangle with zero padding.
+template <bool SYM>
+__global__ void __launch_bounds__(256) cov_tile_kernel(const __grid_constant__ DevProgram prog,
+                                                       const double* __restrict__ Rt, int64_t ldr, int64_t nrows,
+                                                       const double* __restrict__ Ct, int64_t ldc, int64_t ncols,
+                                                       int D, double noise, double* __restrict__ out, int64_t ld,
+                                                       int tiles_n) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* xr = reinterpret_cast<double*>(smem_raw);
+    double* xc = xr + D * TILE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(xc + D * TILE);
+
+    int ti, tj;
+    if (SYM) {
+        lower_tile(blockIdx.x, ti, tj);
+    } else {
+        ti = blockIdx.x / tiles_n;
+        tj = blockIdx.x % tiles_n;
+    }
+    const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
+    stage_tiles(xr, xc, bar, Rt, ldr, row0, Ct, ldc, col0, D);
+
+    const int c0 = 2 * (threadIdx.x & 63);
+    const int ir = threadIdx.x >> 6;
+    for (int rr = 0; rr < TILE / 4; ++rr) {
+        const int r = rr * 4 + ir;
+        const int64_t gi = row0 + r, gj = col0 + c0;
+        double2 v;
+        v.x = eval_program(prog, xc, c0, xr, r);
+        v.y = eval_program(prog, xc, c0 + 1, xr, r);
+        if (SYM) {
+            if (gi == gj) v.x += noise;
+            if (gi == gj + 1) v.y += noise;
+            if (gi >= nrows || gj >= ncols) v.x = (gi == gj) ? 1.0 : 0.0;
+            if (gi >= nrows || gj + 1 >= ncols) v.y = (gi == gj + 1) ? 1.0 : 0.0;
+        } else {
+            if (gi >= nrows || gj >= ncols) v.x = 0.0;
+            if (gi >= nrows || gj + 1 >= ncols) v.y = 0.0;
+        }
+        *reinterpret_cast<double2*>(out + gi * ld + gj) = v;
+    }
+}
+
+static size_t cov_smem(int D) { return (size_t)2 * D * TILE * sizeof(double) + 16; }
+
+void launch_cov_build(const DevProgram& prog, const double* Xt, int64_t N, int64_t Npad, int D, double noise,
+                      double* out, cudaStream_t s) {
+    int T = (int)(Npad / TILE);
+    int ntiles = T * (T + 1) / 2;
+    size_t smem = cov_smem(D);
+    cudaFuncSetAttribute(cov_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cov_tile_kernel<true><<<ntiles, 256, smem, s>>>(prog, Xt, Npad, N, Xt, Npad, N, D, noise, out, Npad, T);
+}
+
+void launch_cov_cross(const DevProgram& prog, const double* Xt, int64_t N, int64_t Npad, const double* Zt, int64_t M,
+                      int64_t Mpad, int D, double* out, cudaStream_t s) {
+    int tm = (int)(Mpad / TILE), tn = (int)(Npad / TILE);
+    size_t smem = cov_smem(D);
+    cudaFuncSetAttribute(cov_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cov_tile_kernel<false><<<tm * tn, 256, smem, s>>>(prog, Zt, Mpad, M, Xt, Npad, N, D, 0.0, out, Npad, tn);
+}
+
+__global__ void cov_self_kernel(const __grid_constant__ DevProgram prog, const double* __restrict__ Zt, int64_t M,
+                                int64_t Mpad, double* __restrict__ kss) {
+    int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double k = 0.0;
+    for (int t = 0; t < prog.nterms; ++t) {
+        double p = prog.coef[t];
+        for (int fi = prog.fbeg[t]; fi < prog.fbeg[t + 1]; ++fi) {
+            const DevFactor& f = prog.f[fi];
+            double z = Zt[f.dim * Mpad + m];
+            p *= factor_value(f, z, z);
+        }
+        k += p;
+    }
+    kss[m] = k;
+}
+
+void launch_cov_self(const DevProgram& prog, const double* Zt, int64_t M, int64_t Mpad, int D, double* kss,
+                     cudaStream_t s) {
+    (void)D;
+    int threads = 128;
+    int blocks = (int)((M + threads - 1) / threads);
+    if (blocks > 0) cov_self_kernel<<<blocks, threads, 0, s>>>(prog, Zt, M, Mpad, kss);
+}
+
+// ---- fused gradient trace ----------------------------------------------------------
+// One CTA per lower tile.  A thread owns a column pair and 32 rows; the tile is
+// walked in two chunks of 16 rows (E = 32 elements per thread).  For each product
+// term: phase 1 forms w_e * P_e (W-weighted term value) per element, phase 2 runs
+// over the term's factors and accumulates P_e-weighted log-derivatives into the
+// parameter slots.  dK is never materialised (the reference stores one dense
+// N x N matrix per parameter, gp/gp.go:93-97,158-163).
+constexpr int GT_E = 32;
+constexpr int GT_SLOTS = kMaxTheta + 1;
+
+__global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__ DevProgram prog,
+                                                         const double* __restrict__ Xt, int64_t ldx,
+                                                         const double* __restrict__ alpha,
+                                                         const double* __restrict__ kinv, int64_t ld,
+                                                         const double* __restrict__ kdiag, int64_t N, int D,
+                                                         double* __restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* xr = reinterpret_cast<double*>(smem_raw);
+    double* xc = xr + D * TILE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(xc + D * TILE);
+    double* pw = reinterpret_cast<double*>(bar + 2);  // [GT_E][256] weighted term values
+    double* ww = pw + GT_E * 256;                     // [GT_E][256] weights w_e * W_e
+    double* acc = ww + GT_E * 256;                    // [8 warps][GT_SLOTS]
+
+    int ti, tj;
+    lower_tile(blockIdx.x, ti, tj);
+    const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = tid; q < 8 * GT_SLOTS; q += 256) acc[q] = 0.0;
+    stage_tiles(xr, xc, bar, Xt, ldx, row0, Xt, ldx, col0, D);  // also a block barrier after acc init
+
+    const double* ktile = (ti == tj) ? kdiag + (int64_t)ti * TILE * TILE : kinv + row0 * ld + col0;
+    const int64_t kld = (ti == tj) ? TILE : ld;
+    const int c0 = 2 * (tid & 63);
+    const int ir = tid >> 6;
+    const int nslot = prog.ntheta;  // slot ntheta = trace of W
+    double trw = 0.0;
+
+    for (int chunk = 0; chunk < 2; ++chunk) {
+        // weights w_e * W_e of this chunk (1 below the diagonal, 1/2 on it, 0 elsewhere)
+#pragma unroll 4
+        for (int e = 0; e < GT_E; e += 2) {
+            const int r = chunk * 64 + (e >> 1) * 4 + ir;
+            const int64_t gi = row0 + r, gj = col0 + c0;
+            const double2 kv = *reinterpret_cast<const double2*>(ktile + (int64_t)r * kld + c0);
+            const double ai = alpha[gi], aj0 = alpha[gj], aj1 = alpha[gj + 1];
+            double w0 = 0.0, w1 = 0.0;
+            if (gi < N && gj < N && gi >= gj) {
+                const double W = ai * aj0 - kv.x;
+                if (gi == gj) {
+                    trw += W;
+                    w0 = 0.5 * W;
+                } else {
+                    w0 = W;
+                }
+            }
+            if (gi < N && gj + 1 < N && gi >= gj + 1) {
+                const double W = ai * aj1 - kv.y;
+                if (gi == gj + 1) {
+                    trw += W;
+                    w1 = 0.5 * W;
+                } else {
+                    w1 = W;
+                }
+            }
+            ww[e * 256 + tid] = w0;
+            ww[(e + 1) * 256 + tid] = w1;
+        }
+        for (int t = 0; t < prog.nterms; ++t) {
+            const int fb = prog.fbeg[t], fe = prog.fbeg[t + 1];
+            // phase 1: weighted term values
+            for (int e = 0; e < GT_E; ++e) {
+                const int r = chunk * 64 + (e >> 1) * 4 + ir;
+                const int c = c0 + (e & 1);
+                double p = prog.coef[t];
+                for (int fi = fb; fi < fe; ++fi) {
+                    const DevFactor& f = prog.f[fi];
+                    p *= factor_value(f, xc[f.dim * TILE + c], xr[f.dim * TILE + r]);
+                }
+                pw[e * 256 + tid] = ww[e * 256 + tid] * p;
+            }
+            // phase 2: per-factor log-derivatives
+            for (int fi = fb; fi < fe; ++fi) {
+                const DevFactor& f = prog.f[fi];
+                double s0 = 0.0, s1 = 0.0;
+                for (int e = 0; e < GT_E; ++e) {
+                    const int r = chunk * 64 + (e >> 1) * 4 + ir;
+                    const int c = c0 + (e & 1);
+                    double g0, g1;
+                    factor_dlog_theta(f, xc[f.dim * TILE + c], xr[f.dim * TILE + r], g0, g1);
+                    const double p = pw[e * 256 + tid];
+                    s0 += p * g0;
+                    s1 += p * g1;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s0 += __shfl_down_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+                }
+                if (lane == 0) {
+                    acc[warp * GT_SLOTS + f.p0] += s0;
+                    if (f.p1 >= 0) acc[warp * GT_SLOTS + f.p1] += s1;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) trw += __shfl_down_sync(0xffffffffu, trw, o);
+    if (lane == 0) acc[warp * GT_SLOTS + nslot] += trw;
+    __syncthreads();
+    if (tid <= nslot) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += acc[w * GT_SLOTS + tid];
+        partial[(int64_t)blockIdx.x * (nslot + 1) + tid] = s;
+    }
+}
+
+// Deterministic second stage: one CTA per slot, fixed summation order.
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restrict__ partial, int nblocks, int nslots,
+                                                          double* __restrict__ out) {
+    __shared__ double sh[256];
+    const int q = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * nslots + q];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[q] = sh[0];
+}
+
+void launch_grad_trace(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,
+                       const double* kdiag, int64_t N, int64_t Npad, int D, double* partial, double* out,
+                       cudaStream_t s) {
+    int T = (int)(Npad / TILE);
+    int ntiles = T * (T + 1) / 2;
+    size_t smem = (size_t)2 * D * TILE * sizeof(double) + 16 + (size_t)2 * GT_E * 256 * sizeof(double) +
+                  (size_t)8 * GT_SLOTS * sizeof(double);
+    cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    grad_trace_kernel<<<ntiles, 256, smem, s>>>(prog, Xt, Npad, alpha, kinv, Npad, kdiag, N, D, partial);
+    grad_reduce_kernel<<<prog.ntheta + 1, 256, 0, s>>>(partial, ntiles, prog.ntheta + 1, out);
+}
+
+// ---- input gradient (with_obs) ---------------------------------------------------
+// One CTA per observation i; for each coordinate d a block reduction over j != i of
+// W_ij * d k(x_i, x_j) / d x_{i,d}.  O(N^2 D F); the reference needs N*D dense
+// N x N matrices and 4N^3 flops each for the same numbers (gp/gp.go:93-94,118-129).
+__global__ void __launch_bounds__(256) grad_inputs_kernel(const __grid_constant__ DevProgram prog,
+                                                          const double* __restrict__ Xt, int64_t ldx,
+                                                          const double* __restrict__ alpha,
+                                                          const double* __restrict__ kinv, int64_t ld,
+                                                          const double* __restrict__ kdiag, int64_t N, int D,
+                                                          double* __restrict__ gx) {
+    __shared__ double sh[256];
+    const int64_t i = blockIdx.x;
+    const double ai = alpha[i];
+    for (int d = 0; d < D; ++d) {
+        double s = 0.0;
+        for (int64_t j = threadIdx.x; j < N; j += 256) {
+            if (j == i) continue;
+            const int64_t hi = i > j ? i : j, lo = i > j ? j : i;
+            const int64_t th = hi / TILE, tl = lo / TILE;
+            double kv = (th == tl) ? kdiag[th * TILE * TILE + (hi % TILE) * TILE + (lo % TILE)] : kinv[hi * ld + lo];
+            const double W = ai * alpha[j] - kv;
+            double dk = 0.0;
+            for (int t = 0; t < prog.nterms; ++t) {
+                double p = prog.coef[t];
+                double g = 0.0;
+                for (int fi = prog.fbeg[t]; fi < prog.fbeg[t + 1]; ++fi) {
+                    const DevFactor& f = prog.f[fi];
+                    const double xa = Xt[f.dim * ldx + i], xb = Xt[f.dim * ldx + j];
+                    p *= factor_value(f, xa, xb);
+                    if (f.dim == d && f.kind != F_PARAM) g += factor_dlog_xa(f, xa, xb);
+                }
+                dk += p * g;
+            }
+            s += W * dk;
+        }
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) gx[i * D + d] = sh[0];
+        __syncthreads();
+    }
+}
+
+void launch_grad_inputs(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,
+                        const double* kdiag, int64_t N, int64_t Npad, int D, double* gx, cudaStream_t s) {
+    if (N <= 0) return;
+    grad_inputs_kernel<<<(int)N, 256, 0, s>>>(prog, Xt, Npad, alpha, kinv, Npad, kdiag, N, D, gx);
+}
+
+}  // namespace gogp

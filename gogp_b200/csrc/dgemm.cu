@@ -1,0 +1,232 @@
+// FP64 tensor-core GEMM  C = beta*C + alpha * A * B^T  for sm_100a.
+//
+// This is the dense contraction behind every O(N^3) step of the path: the
+// trailing SYRK/GEMM updates of the Cholesky (reference: gp.L.Factorize(K),
+// gp/gp.go:228), the triangular inverse and the K^-1 = L^-T L^-1 product that
+// replace the reference's per-parameter L.SolveTo (gp/gp.go:454,480), and the
+// multi-right-hand-side solve of Produce (gp/gp.go:337-340).
+//
+// Blackwell's tcgen05/TMEM path has no FP64 kind (ptxas rejects .kind::f64), so
+// the FP64 tensor pipe is reached through mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).
+// CTA tile 128x128, BK = 16, 4-stage cp.async ring (160 KB smem), 8 warps as
+// 2 (M) x 4 (N), warp tile 64x32 = 8x4 DMMA fragments (64 FP64 accumulators per
+// thread).  Both operands are row-major with k contiguous ("NT"), staged as
+// [row][k] with a row pitch of 20 doubles: a half-warp's fragment read touches
+// rows r..r+3 x k..k+3 -> word offsets (20r + k)*2, all 32 banks distinct.
+#include <cstdio>
+
+#include "kernels.h"
+#include "kexpr.cuh"
+
+namespace gogp {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int PITCH = BK + 4;                      // doubles
+constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;   // A tile then B tile
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+
+struct GemmArgs {
+    double* C;
+    const double* A;
+    const double* B;
+    double* cdiag;
+    int64_t ldc, lda, ldb;
+    int tm, tn;   // tiles
+    int k;        // elements
+    int mode;
+    double alpha, beta;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(const GemmArgs g) {
+    extern __shared__ __align__(128) double smem[];
+    int ti, tj;
+    if (g.mode & GEMM_LOWER) {
+        lower_tile(blockIdx.x, ti, tj);
+    } else {
+        ti = blockIdx.x / g.tn;
+        tj = blockIdx.x % g.tn;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+    const int64_t row0 = (int64_t)ti * BM, col0 = (int64_t)tj * BN;
+    const int k_lo = (g.mode & GEMM_KTRI) ? ti * BM : 0;
+    const int nk = (g.k - k_lo) / BK;
+
+    const double* Ag = g.A + row0 * g.lda + k_lo;
+    const double* Bg = g.B + col0 * g.ldb + k_lo;
+
+    // each thread copies 4 16-byte chunks of A and 4 of B per stage
+    auto load_stage = [&](int stage, int kt) {
+        double* sa = smem + stage * STAGE_DOUBLES;
+        double* sb = sa + BM * PITCH;
+        const int64_t koff = (int64_t)kt * BK;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = tid + q * 256;
+            const int r = c >> 3, kc = (c & 7) * 2;
+            cp_async16(sa + r * PITCH + kc, Ag + (int64_t)r * g.lda + koff + kc);
+            cp_async16(sb + r * PITCH + kc, Bg + (int64_t)r * g.ldb + koff + kc);
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nxt = kt + STAGES - 1;
+            if (nxt < nk) load_stage(nxt % STAGES, nxt);
+            cp_async_commit();
+        }
+        const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * 64 + fr) * PITCH + fk;
+        const double* sb = smem + (kt % STAGES) * STAGE_DOUBLES + BM * PITCH + (wn * 32 + fr) * PITCH + fk;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = sa[i * 8 * PITCH + ks * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sb[j * 8 * PITCH + ks * 4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread holds C[row][col..col+1] per fragment
+    double* Cb;
+    int64_t ldc;
+    if ((g.mode & GEMM_DIAG_OUT) && ti == tj) {
+        Cb = g.cdiag + (int64_t)ti * BM * BN;
+        ldc = BN;
+    } else {
+        Cb = g.C + row0 * g.ldc + col0;
+        ldc = g.ldc;
+    }
+    const int er = wm * 64 + fr, ec = wn * 32 + 2 * fk;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double2* p = reinterpret_cast<double2*>(Cb + (int64_t)(er + i * 8) * ldc + ec + j * 8);
+            double2 v;
+            v.x = g.alpha * acc[i][j][0];
+            v.y = g.alpha * acc[i][j][1];
+            if (g.beta != 0.0) {
+                const double2 c = *p;
+                v.x += g.beta * c.x;
+                v.y += g.beta * c.y;
+            }
+            *p = v;
+        }
+}
+
+// ---- FP64 peak microbenchmarks (registers only) --------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s;
+}
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* sink) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-9 + i;
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) sink[0] = s;
+}
+
+constexpr int PEAK_CTAS_PER_SM = 4;
+
+}  // namespace
+
+void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
+                     int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+        configured = true;
+    }
+    GemmArgs g;
+    g.C = C;
+    g.A = A;
+    g.B = B;
+    g.cdiag = cdiag;
+    g.ldc = ldc;
+    g.lda = lda;
+    g.ldb = ldb;
+    g.tm = (int)(m / BM);
+    g.tn = (int)(n / BN);
+    g.k = (int)k;
+    g.mode = mode;
+    g.alpha = alpha;
+    g.beta = beta;
+    int ntiles = (mode & GEMM_LOWER) ? g.tm * (g.tm + 1) / 2 : g.tm * g.tn;
+    if (ntiles <= 0 || k <= 0) return;
+    dgemm_nt_kernel<<<ntiles, 256, GEMM_SMEM, s>>>(g);
+}
+
+void launch_fp64_peak(int which, int iters, double* sink, cudaStream_t s) {
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (which == 0)
+        dmma_peak_kernel<<<nsm * PEAK_CTAS_PER_SM, 256, 0, s>>>(iters, sink);
+    else
+        dfma_peak_kernel<<<nsm * PEAK_CTAS_PER_SM, 256, 0, s>>>(iters, sink);
+}
+
+double fp64_peak_flops_per_launch(int which, int iters, int nsm) {
+    const double warps = (double)nsm * PEAK_CTAS_PER_SM * 8;
+    if (which == 0) return warps * iters * 16.0 * (8 * 8 * 4 * 2);  // DMMA m8n8k4
+    return warps * 32.0 * iters * 16.0 * 2;                       // DFMA
+}
+
+}  // namespace gogp

@@ -1,0 +1,75 @@
+// Host-callable launchers of the sm_100a kernels (one translation unit each).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "program.h"
+
+namespace gogp {
+
+constexpr int TILE = 128;  // all dense blocks are 128 x 128 FP64 tiles
+
+// ---- cov.cu ----------------------------------------------------------------
+// X (N x D row-major) -> Xt ([D][Npad], zero padded)
+void launch_transpose_x(const double* X, double* Xt, int64_t N, int64_t Npad, int D, cudaStream_t s);
+// K = k(X, X) + noise I on the lower tiles of out (Npad x Npad, ld = Npad); the
+// padding block is the identity.  gp/gp.go:109-156,220-225.
+void launch_cov_build(const DevProgram& prog, const double* Xt, int64_t N, int64_t Npad, int D, double noise,
+                      double* out, cudaStream_t s);
+// out[m][i] = k(xa = x_i, xb = z_m), Mpad x Npad (ld = Npad), zero padded.  gp/gp.go:322-332.
+void launch_cov_cross(const DevProgram& prog, const double* Xt, int64_t N, int64_t Npad, const double* Zt, int64_t M,
+                      int64_t Mpad, int D, double* out, cudaStream_t s);
+// kss[m] = k(z_m, z_m).  gp/gp.go:270-278.
+void launch_cov_self(const DevProgram& prog, const double* Zt, int64_t M, int64_t Mpad, int D, double* kss,
+                     cudaStream_t s);
+// Fused gradient trace, gp/gp.go:434-486 without materialising dK:
+//   out[q]      = sum_{i>j} W_ij dK_q,ij + 0.5 sum_i W_ii dK_q,ii  (similarity parameters, log scale)
+//   out[ntheta] = sum_i W_ii,   W = alpha alpha^T - K^-1
+// Kinv: strictly-lower tiles in `kinv` (ld = Npad), diagonal tiles in `kdiag` ([T][128][128]).
+// partial: scratch of ntiles * (ntheta+1) doubles.
+void launch_grad_trace(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,
+                       const double* kdiag, int64_t N, int64_t Npad, int D, double* partial, double* out,
+                       cudaStream_t s);
+// Input gradient for Observe's with_obs layout (gp/gp.go:118-129, 488-493):
+//   gx[i*D+d] = sum_{j != i} W_ij d k(x_i, x_j)/d x_{i,d}
+void launch_grad_inputs(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,
+                        const double* kdiag, int64_t N, int64_t Npad, int D, double* gx, cudaStream_t s);
+
+// ---- dgemm.cu ----------------------------------------------------------------
+enum GemmMode : int {
+    GEMM_FULL = 0,
+    GEMM_LOWER = 1,     // only tiles ti >= tj (SYRK / LAUUM)
+    GEMM_KTRI = 2,      // A is upper triangular w.r.t. its own origin: k starts at ti*128
+    GEMM_DIAG_OUT = 4,  // diagonal tiles go to cdiag ([T][128][128]) instead of C
+};
+// C[i][j] = beta*C[i][j] + alpha * sum_k A[i][k] B[j][k]; all of m, n, k multiples of 128.
+void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
+                     int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s);
+void launch_fp64_peak(int which, int iters, double* sink, cudaStream_t s);  // microbenchmark kernels
+double fp64_peak_flops_per_launch(int which, int iters, int nsm);
+
+// ---- leaf.cu -------------------------------------------------------------------
+// Cholesky of the 128x128 diagonal tile at A (ld), in place (lower; upper zeroed),
+// and its inverse into winv (128x128 row-major lower).  info: 0 or 1-based index
+// of the first non-positive pivot (global index = base + local).
+void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s);
+// dst tile (ld) = winv^T (upper triangular, strictly-lower zeroed).
+void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t s);
+// Blocked triangular solves with the tile inverses.  fwd: out = L^-1 rhs; bwd: out = L^-T rhs.
+// rhs (Npad) is destroyed; out must not alias it.
+void launch_trsv_lower(const double* L, int64_t ld, const double* winv, double* rhs, double* out, int64_t Npad,
+                       bool transposed, cudaStream_t s, int64_t* launches);
+// v[i] = value for i in [0, n)
+void launch_fill(double* v, int64_t n, double value, cudaStream_t s);
+// pseudo-random fill in (-0.5, 0.5) for microbenchmarks
+void launch_fill_pattern(double* v, int64_t n, cudaStream_t s);
+// out[0] = sum_i log L_ii (i < N), out[1] = sum_i y_i alpha_i
+void launch_logdet_dot(const double* L, int64_t ld, const double* y, const double* alpha, int64_t N, double* out,
+                       cudaStream_t s);
+// row reductions of a Mpad x Npad matrix: out[m] = sum_i B[m][i] * (v ? v[i] : B[m][i])
+void launch_row_reduce(const double* B, int64_t ld, int64_t rows, int64_t cols, const double* v, double* out,
+                       cudaStream_t s);
+// mirror helper for debug fetches: out (N x N) from lower tiles (+ optional diagonal tiles)
+void launch_gather_sym(const double* src, int64_t ld, const double* diag, int64_t N, double* out, cudaStream_t s);
+
+}  // namespace gogp

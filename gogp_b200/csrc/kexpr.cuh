@@ -1,0 +1,145 @@
+// Device-side evaluation of the canonical kernel expression (program.h).
+//
+// Values follow the reference's arithmetic operation by operation
+// (kernel/kernel.go:23-26, 44-47, 70-73, 89-92); partials are closed forms of
+// what the reference's AD tape returns (kernel/ad/kernel.go), expressed as
+// log-derivatives so a product term needs only its value:
+//     d(prod)/d log(theta_q) = prod * theta_q * (d f/d theta_q) / f
+#pragma once
+#include "program.h"
+
+namespace gogp {
+
+#define GOGP_SQRT3 1.7320508075688772
+#define GOGP_SQRT5 2.2360679774997900
+#define GOGP_PI 3.14159265358979323846
+
+__device__ __forceinline__ double factor_value(const DevFactor& f, double xa, double xb) {
+    switch (f.kind) {
+        case F_PARAM:
+            return f.a0;
+        case F_NORMAL: {
+            double d = (xa - xb) / f.a0;
+            return exp(-d * d / 2);
+        }
+        case F_PERIODIC: {
+            double d = sin(GOGP_PI * fabs(xa - xb) / f.a1) / f.a0;
+            return exp(-2 * d * d);
+        }
+        case F_MATERN32: {
+            double d = fabs(xa - xb) / f.a0;
+            return (1 + GOGP_SQRT3 * d) * exp(-GOGP_SQRT3 * d);
+        }
+        default: {  // F_MATERN52
+            double d = fabs(xa - xb) / f.a0;
+            return (1 + GOGP_SQRT5 * d + f.c * d * d) * exp(-GOGP_SQRT5 * d);
+        }
+    }
+}
+
+// theta_q * (d f / d theta_q) / f for the (up to) two parameters of a factor.
+__device__ __forceinline__ void factor_dlog_theta(const DevFactor& f, double xa, double xb, double& g0, double& g1) {
+    g1 = 0.0;
+    switch (f.kind) {
+        case F_PARAM:
+            g0 = 1.0;
+            return;
+        case F_NORMAL: {
+            double d = (xa - xb) / f.a0;
+            g0 = d * d;
+            return;
+        }
+        case F_PERIODIC: {
+            double u = GOGP_PI * fabs(xa - xb) / f.a1;
+            double s, c;
+            sincos(u, &s, &c);
+            double d = s / f.a0;
+            g0 = 4 * d * d;
+            g1 = 4 * d * c * u / f.a0;
+            return;
+        }
+        case F_MATERN32: {
+            double d = fabs(xa - xb) / f.a0;
+            g0 = 3 * d * d / (1 + GOGP_SQRT3 * d);
+            return;
+        }
+        default: {
+            double d = fabs(xa - xb) / f.a0;
+            g0 = d * d * (5 - 2 * f.c + GOGP_SQRT5 * f.c * d) / (1 + GOGP_SQRT5 * d + f.c * d * d);
+            return;
+        }
+    }
+}
+
+// (d f / d xa) / f ;  d/d xb is its negative for every stock (stationary) leaf.
+__device__ __forceinline__ double factor_dlog_xa(const DevFactor& f, double xa, double xb) {
+    double r = xa - xb;
+    double sg = (r > 0) - (r < 0);
+    switch (f.kind) {
+        case F_PARAM:
+            return 0.0;
+        case F_NORMAL: {
+            double d = r / f.a0;
+            return -d / f.a0;
+        }
+        case F_PERIODIC: {
+            double u = GOGP_PI * fabs(r) / f.a1;
+            double s, c;
+            sincos(u, &s, &c);
+            double d = s / f.a0;
+            return -4 * d * c * GOGP_PI * sg / (f.a0 * f.a1);
+        }
+        case F_MATERN32: {
+            double d = fabs(r) / f.a0;
+            return -3 * d * sg / (f.a0 * (1 + GOGP_SQRT3 * d));
+        }
+        default: {
+            double d = fabs(r) / f.a0;
+            return -d * (5 - 2 * f.c + GOGP_SQRT5 * f.c * d) * sg / (f.a0 * (1 + GOGP_SQRT5 * d + f.c * d * d));
+        }
+    }
+}
+
+// ---- TMA (bulk async copy) + mbarrier helpers -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D bulk copy global -> shared through the TMA unit (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Lower-triangular tile index b -> (ti, tj), ti >= tj, rows ascending.
+__device__ __forceinline__ void lower_tile(int b, int& ti, int& tj) {
+    int t = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while (t * (t + 1) / 2 > b) --t;
+    while ((t + 1) * (t + 2) / 2 <= b) ++t;
+    ti = t;
+    tj = b - t * (t + 1) / 2;
+}
+
+}  // namespace gogp

@@ -1,0 +1,248 @@
+"""Host-side mirror of gp.GP and gp.Model (reference gp/gp.go, gp/model.go) over
+the C-ABI.  Same names, argument layout and error behaviour as the reference,
+so the parity tests read like gp/gp_test.go:
+
+    g = GP(NDim=1, Simil=kernel.Normal, Noise=kernel.ConstantNoise(0.1))
+    ll = g.Observe(x)          # x = [log theta | X flat | Y]  or  [log theta]
+    dll = g.Gradient()
+    err = g.Absorb(X, Y); mu, sigma, err = g.Produce(Z)
+
+The Go wrapper a maintainer would add is go/gp/gp.go; this
+module is what can be executed where no Go toolchain exists.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from . import kernel as _kernel
+
+
+class GoGPError(Exception):
+    """An ``error`` value of the reference (Absorb / Produce return it)."""
+
+    def __init__(self, status, msg):
+        Exception.__init__(self, msg)
+        self.status = status
+
+
+class GoGPPanic(RuntimeError):
+    """Where the reference panics (Observe: gp/gp.go:398-405)."""
+
+    def __init__(self, status, msg):
+        RuntimeError.__init__(self, msg)
+        self.status = status
+
+
+def _flat(x, ndim):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64)).reshape(-1)
+    if ndim and a.size % ndim:
+        raise ValueError("input size is not a multiple of NDim")
+    return a
+
+
+class GP:
+    """gp.GP (gp/gp.go:20-38)."""
+
+    def __init__(self, NDim=1, Simil=None, Noise=None, ThetaSimil=None, ThetaNoise=None, X=None, Y=None,
+                 Parallel=False, Device=0):
+        self.NDim = NDim
+        self.Simil = Simil
+        self.Noise = Noise
+        self.ThetaSimil = [] if ThetaSimil is None else list(ThetaSimil)
+        self.ThetaNoise = [] if ThetaNoise is None else list(ThetaNoise)
+        self.X = [] if X is None else X
+        self.Y = [] if Y is None else Y
+        self.Parallel = Parallel  # the GPU build is the parallel path; kept for API parity (gp/gp.go:31)
+        self.Device = Device
+        self._h = None
+        self._key = None
+        self._with_obs = False
+        self._n = 0
+
+    # -- handle management ------------------------------------------------------
+    def _handle(self):
+        key = (self.NDim, id(self.Simil), id(self.Noise), self.Device)
+        if self._h is not None and key == self._key:
+            return self._h
+        self.close()
+        if self.Simil is None:
+            raise GoGPPanic(_lib.BAD_ARGUMENT, "GP.Simil is nil")
+        L = _lib.lib()
+        sd = self.Simil.Descriptor()
+        if self.Noise is not None:
+            nd = self.Noise.Descriptor()
+            nn, ntn = len(nd), self.Noise.NTheta()
+        else:
+            nd, nn, ntn = None, 0, 0  # defaults(): ConstantNoise(1e-5), gp/gp.go:46-48
+        h = C.c_void_p()
+        st = L.gogp_create(self.NDim, sd, len(sd), self.Simil.NTheta(), nd, nn, ntn, self.Device, C.byref(h))
+        if st != _lib.OK:
+            msg = L.gogp_last_error(h).decode() if h else "gogp_create failed"
+            if h:
+                L.gogp_destroy(h)
+            raise GoGPPanic(st, msg)
+        self._h, self._key = h, key
+        return h
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().gogp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, st):
+        return _lib.lib().gogp_last_error(self._h).decode() or _lib.lib().gogp_status_string(st).decode()
+
+    def _nts(self):
+        return self.Simil.NTheta()
+
+    def _ntn(self):
+        return self.Noise.NTheta() if self.Noise is not None else 0
+
+    def _defaults(self):
+        # gp/gp.go:45-57
+        if len(self.ThetaSimil) == 0:
+            self.ThetaSimil = [0.0] * self._nts()
+        if len(self.ThetaNoise) == 0:
+            self.ThetaNoise = [0.0] * self._ntn()
+
+    # -- gp/gp.go:80-87 ------------------------------------------------------------
+    def Absorb(self, x, y):
+        """Returns None or a GoGPError (the reference returns ``err``)."""
+        self._defaults()
+        self.X, self.Y = x, y
+        h = self._handle()
+        X = _flat(x, self.NDim)
+        Y = _flat(y, 0)
+        n = len(Y)
+        if X.size != n * self.NDim:
+            return GoGPError(_lib.BAD_ARGUMENT, "len(x) != len(y)")
+        ts = np.array(self.ThetaSimil, dtype=np.float64)
+        tn = np.array(self.ThetaNoise, dtype=np.float64)
+        st = _lib.lib().gogp_absorb(h, _lib.dptr(ts), _lib.dptr(tn), _lib.dptr(X), _lib.dptr(Y), n)
+        self._with_obs, self._n = False, n
+        if st != _lib.OK:
+            return GoGPError(st, self._err(st))
+        return None
+
+    # -- gp/gp.go:244-253 ------------------------------------------------------------
+    def LML(self):
+        out = C.c_double(0.0)
+        st = _lib.lib().gogp_lml(self._handle(), C.byref(out))
+        if st != _lib.OK:
+            raise GoGPPanic(st, self._err(st))
+        return out.value
+
+    # -- gp/gp.go:258-360 ------------------------------------------------------------
+    def Produce(self, x):
+        """-> (mu, sigma, err)"""
+        self._defaults()
+        h = self._handle()
+        Z = _flat(x, self.NDim)
+        m = Z.size // self.NDim
+        mu = np.zeros(m)
+        sigma = np.zeros(m)
+        st = _lib.lib().gogp_produce(h, _lib.dptr(Z), m, _lib.dptr(mu), _lib.dptr(sigma))
+        if st != _lib.OK:
+            return None, None, GoGPError(st, self._err(st))
+        return mu, sigma, None
+
+    # -- gp/gp.go:374-413 ------------------------------------------------------------
+    def Observe(self, x):
+        """x: float64 numpy array, [log theta] or [log theta | X flat | Y].  As in
+        the reference the parameter prefix is exponentiated in place for the
+        duration of the call and logged back (gp/gp.go:378-381, 408-410)."""
+        self._defaults()
+        h = self._handle()
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous):
+            raise TypeError("Observe takes a contiguous float64 numpy array")
+        nts, ntn, D = self._nts(), self._ntn(), self.NDim
+        P = nts + ntn
+        if len(x) < P:
+            raise GoGPPanic(_lib.BAD_ARGUMENT, "len(x)")
+        theta = x[:P]
+        logt = theta.copy()
+        np.exp(theta, out=theta)
+        try:
+            self.ThetaSimil = list(theta[:nts])
+            self.ThetaNoise = list(theta[nts:P])
+            rest = x[P:]
+            self._with_obs = len(rest) > 0
+            if self._with_obs:
+                n = len(rest) // (D + 1)
+                if n * (D + 1) != len(rest):
+                    raise GoGPPanic(_lib.BAD_ARGUMENT, "len(x)")  # gp/gp.go:398-400
+                self.X = rest[:n * D].reshape(n, D)  # views into x, as the reference aliases
+                self.Y = rest[n * D:]
+                X, Y = rest[:n * D], rest[n * D:]
+            else:
+                X = _flat(self.X, D)
+                Y = _flat(self.Y, 0)
+                n = len(Y)
+                if X.size != n * D:
+                    raise GoGPPanic(_lib.BAD_ARGUMENT, "len(gp.X) != len(gp.Y)")
+            out = C.c_double(0.0)
+            st = _lib.lib().gogp_observe(h, _lib.dptr(logt), 1 if self._with_obs else 0, _lib.dptr(X), _lib.dptr(Y),
+                                         n, C.byref(out))
+            self._n = n
+            if st != _lib.OK:
+                raise GoGPPanic(st, self._err(st))  # panic(err), gp/gp.go:403-405
+        finally:
+            np.log(theta, out=theta)
+        return out.value
+
+    # -- gp/gp.go:418-499 ------------------------------------------------------------
+    def Gradient(self):
+        h = self._handle()
+        P = self._nts() + self._ntn()
+        n = P + (self._n * (self.NDim + 1) if self._with_obs else 0)
+        grad = np.zeros(n)
+        st = _lib.lib().gogp_gradient(h, _lib.dptr(grad), n)
+        if st != _lib.OK:
+            raise GoGPPanic(st, self._err(st))
+        return grad
+
+    # -- extras over the C-ABI ---------------------------------------------------------
+    def PhaseTimes(self):
+        ms = np.zeros(len(_lib.PHASES))
+        _lib.lib().gogp_phase_times(self._handle(), _lib.dptr(ms))
+        return dict(zip(_lib.PHASES, ms.tolist()))
+
+    def Launches(self):
+        return int(_lib.lib().gogp_launch_count(self._handle()))
+
+    def Alpha(self):
+        a = np.zeros(self._n)
+        st = _lib.lib().gogp_get_alpha(self._handle(), _lib.dptr(a), self._n)
+        if st != _lib.OK:
+            raise GoGPPanic(st, self._err(st))
+        return a
+
+
+class Model:
+    """gp.Model (gp/model.go:9-28): GP plus priors on the hyper-parameters.
+    ``Priors`` is any object with Observe(x) -> float and Gradient() -> array."""
+
+    def __init__(self, GP, Priors):
+        self.GP = GP
+        self.Priors = Priors
+        self.gGrad = None
+        self.pGrad = None
+
+    def Observe(self, x):
+        gll = self.GP.Observe(x)
+        self.gGrad = self.GP.Gradient()
+        pll = self.Priors.Observe(x)
+        self.pGrad = np.asarray(self.Priors.Gradient(), dtype=np.float64)
+        return gll + pll
+
+    def Gradient(self):
+        self.gGrad[:len(self.pGrad)] += self.pGrad
+        return self.gGrad

@@ -1,0 +1,172 @@
+/*
+ * gogp_b200 -- C-ABI of the B200-native GP hot path.
+ *
+ * This is the drop-in boundary for GoGP's gp.GP (reference gp/gp.go): the Go
+ * package keeps its public surface (gp.GP{NDim, Simil, Noise}, Observe,
+ * Gradient, Absorb, LML, Produce; gp.Model) and reaches the GPU only through
+ * the entry points below (cgo binding: INTEGRATION.md, go/gp/gp.go).
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns a
+ *     gogp_status; gogp_last_error(h) has the text of the last failure;
+ *   - every pointer is a HOST pointer to float64 data owned by the caller;
+ *     nothing is retained after return (cgo pointer rules);
+ *   - inputs X, Z are row-major, one point per row (the flattening of Go's
+ *     [][]float64);
+ *   - a handle is bound to one CUDA device and owns one stream; handles are
+ *     not thread-safe (neither is gp.GP) but distinct handles may be used
+ *     concurrently from different OS threads (multi-start restarts);
+ *   - there is no CPU fallback: without a CUDA device gogp_create fails with
+ *     GOGP_CUDA_ERROR.
+ */
+#ifndef GOGP_B200_H
+#define GOGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GOGP_OK = 0,
+    GOGP_BAD_ARGUMENT = 1,          /* Observe's panic("len(x)"), gp/gp.go:398-400 */
+    GOGP_NOT_POSITIVE_DEFINITE = 2, /* Factorize(K) == false, gp/gp.go:228-230 */
+    GOGP_ILL_CONDITIONED = 3,       /* reserved: gonum's Condition error, gp/gp.go:233-236 */
+    GOGP_CUDA_ERROR = 4,
+    GOGP_NCCL_ERROR = 5,
+    GOGP_OUT_OF_MEMORY = 6,
+    GOGP_NOT_READY = 7,             /* Gradient/LML/Produce before Observe/Absorb */
+    GOGP_UNSUPPORTED = 8            /* kernel expression too large for the descriptor */
+} gogp_status;
+
+/*
+ * Kernel-expression descriptor: a postfix program over a value stack.  It
+ * replaces the per-element dynamic dispatch into gp.Kernel.Observe
+ * (gp/gp.go:14-17, :110-111, :134-135) plus the AD backward pass
+ * (model.Gradient, gp/gp.go:113,137): a user Simil written in Go cannot run on
+ * the device, so the stock kernels of kernel/kernel.go and kernel/noise.go and
+ * their scaled sums and products are described, not called.
+ *
+ * Parameter indices refer to the kernel's own theta vector (ThetaSimil for the
+ * similarity program, ThetaNoise for the noise program); a parameter enters a
+ * leaf as scale * theta[param] (tutorial/hyperpriors/kernel/kernel.go:24 uses
+ * 10*x[p]).  `dim` selects the input coordinate the 1-D stock kernel acts on.
+ */
+typedef enum {
+    GOGP_OP_CONST = 0,           /* push `constant` */
+    GOGP_OP_PARAM = 1,           /* push scale[0] * theta[param[0]] */
+    GOGP_OP_ADD = 2,             /* pop b, pop a, push a + b */
+    GOGP_OP_MUL = 3,             /* pop b, pop a, push a * b */
+    GOGP_OP_NORMAL = 4,          /* kernel.Normal.Cov(l, xa, xb)       kernel/kernel.go:23-26 */
+    GOGP_OP_PERIODIC = 5,        /* kernel.Periodic.Cov(l, p, xa, xb)  kernel/kernel.go:44-47 */
+    GOGP_OP_MATERN32 = 6,        /* kernel.Matern32.Cov(l, xa, xb)     kernel/kernel.go:70-73 */
+    GOGP_OP_MATERN52 = 7,        /* kernel.Matern52.Cov as shipped: 5/3 == 1, kernel/kernel.go:89-92 */
+    GOGP_OP_MATERN52_TEXTBOOK = 8 /* (1 + sqrt5 d + 5/3 d^2) exp(-sqrt5 d); not in the reference */
+} gogp_op_kind;
+
+typedef struct {
+    uint8_t kind;      /* gogp_op_kind */
+    uint8_t dim;       /* input coordinate for leaves, 0 <= dim < ndim */
+    int16_t param[2];  /* theta indices: [0] = length scale l (or the PARAM), [1] = period p */
+    double scale[2];   /* constant multipliers of those parameters (1.0 when unused) */
+    double constant;   /* GOGP_OP_CONST value */
+} gogp_op;
+
+/* The noise program may only use CONST, PARAM, ADD, MUL (every noise kernel the
+ * reference ships is input-independent: kernel/noise.go:21-53).  UniformNoise is
+ * PARAM(0) PARAM(0) MUL; ConstantNoise(c) is CONST(c*c) with ntheta_noise 0;
+ * tutorial/anynoise's noise is CONST(1e-5) with ntheta_noise 1. */
+
+typedef struct gogp_handle gogp_handle;
+
+/* Phases reported by gogp_phase_times (milliseconds of device time, CUDA events,
+ * for the most recent Observe/Absorb, Gradient and Produce). */
+enum {
+    GOGP_PHASE_UPLOAD = 0, /* host->device copies of theta/X/Y */
+    GOGP_PHASE_BUILD = 1,  /* covariance build K(X,X)+noise           gp/gp.go:109-225 */
+    GOGP_PHASE_POTRF = 2,  /* Cholesky                                 gp/gp.go:228 */
+    GOGP_PHASE_SOLVE = 3,  /* alpha = K^-1 y, logdet, y.alpha          gp/gp.go:232-236,250-251 */
+    GOGP_PHASE_POTRI = 4,  /* K^-1 from L (gradient only)              gp/gp.go:454,480 */
+    GOGP_PHASE_TRACE = 5,  /* fused trace 0.5 tr((aa^T-K^-1) dK)       gp/gp.go:434-486 */
+    GOGP_PHASE_PREDICT = 6,/* Produce                                  gp/gp.go:258-360 */
+    GOGP_NPHASE = 7
+};
+
+/* gp.GP{NDim, Simil, Noise} (gp/gp.go:20-23).  noise == NULL / n_noise_ops == 0
+ * selects the reference default ConstantNoise(1e-5) (gp/gp.go:43-48). */
+gogp_status gogp_create(int ndim,
+                        const gogp_op* simil, int n_simil_ops, int ntheta_simil,
+                        const gogp_op* noise, int n_noise_ops, int ntheta_noise,
+                        int device, gogp_handle** out);
+void gogp_destroy(gogp_handle* h);
+
+/* Assigning the fields gp.X, gp.Y (tutorial/tutorial.go:114-115) for the
+ * hyper-parameters-only mode of Observe.  X is N x ndim row-major. */
+gogp_status gogp_set_data(gogp_handle* h, const double* X, const double* Y, int64_t N);
+
+/* gp.GP.Observe (gp/gp.go:374-413).  log_theta holds ntheta_simil+ntheta_noise
+ * log-scale hyper-parameters.  with_obs != 0 is the "inputs are inferred too"
+ * layout: X (N x ndim) and Y (N) are the tail of Observe's argument and the
+ * following gogp_gradient returns the full [theta | X | Y] gradient.  With
+ * with_obs == 0, X/Y may be NULL (use the data set by gogp_set_data) or given
+ * (equivalent to gogp_set_data followed by the call).  Returns the log marginal
+ * likelihood in *lml.  GOGP_NOT_POSITIVE_DEFINITE is where the reference panics. */
+gogp_status gogp_observe(gogp_handle* h, const double* log_theta, int with_obs,
+                         const double* X, const double* Y, int64_t N, double* lml);
+
+/* gp.GP.Gradient (gp/gp.go:418-499): gradient of the last Observe with respect
+ * to its argument, layout [log theta_simil | log theta_noise | X flat | Y];
+ * len must be ntheta (hyper-parameters only) or ntheta + N*(ndim+1) (with_obs).
+ * K^-1 is computed here, lazily, so value-only Observe calls cost one Cholesky. */
+gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len);
+
+/* gp.GP.Absorb (gp/gp.go:80-87): natural-scale parameters, no gradient. */
+gogp_status gogp_absorb(gogp_handle* h, const double* theta_simil, const double* theta_noise,
+                        const double* X, const double* Y, int64_t N);
+
+/* gp.GP.LML (gp/gp.go:244-253) of the absorbed observations; 0 when N == 0. */
+gogp_status gogp_lml(gogp_handle* h, double* lml);
+
+/* gp.GP.Produce (gp/gp.go:258-360): posterior mean and standard deviation of
+ * the latent function at M points Z (M x ndim).  N == 0 gives the prior.  The
+ * radicand is clamped at 0 (the reference takes sqrt of a possibly tiny
+ * negative number, gp/gp.go:356; its own goldens expect 0 there). */
+gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu, double* sigma);
+
+/* The stored results the reference lets a user keep (gp/gp.go:255-257):
+ * alpha (N) and, optionally, the N x N row-major lower Cholesky factor. */
+gogp_status gogp_get_alpha(gogp_handle* h, double* alpha, int64_t N);
+gogp_status gogp_get_factor(gogp_handle* h, double* L, int64_t N);
+
+const char* gogp_last_error(const gogp_handle* h);
+const char* gogp_status_string(gogp_status s);
+gogp_status gogp_phase_times(const gogp_handle* h, double* ms /* GOGP_NPHASE */);
+
+/* Number of kernels this library has launched on the handle's stream since
+ * creation (bench.py's gpu_launches). */
+int64_t gogp_launch_count(const gogp_handle* h);
+
+/* Test/diagnostic access to device state: what = 0 K (before factorisation is
+ * not kept; returns the factor buffer), 1 L, 2 K^-1 (after gogp_gradient).
+ * out is N x N row-major, lower triangle valid, upper mirrored. */
+gogp_status gogp_debug_fetch(gogp_handle* h, int what, double* out, int64_t N);
+
+/* Covariance build only (no factorisation): fills out (N x N row-major,
+ * symmetric) with K(X,X)+noise for natural-scale parameters.  Test hook for
+ * the build kernel and the descriptor interpreter. */
+gogp_status gogp_debug_build(gogp_handle* h, const double* theta_simil, const double* theta_noise,
+                             const double* X, int64_t N, double* out);
+
+/* FP64 throughput microbenchmarks on the handle's device: which = 0 DMMA
+ * (mma.sync m8n8k4 f64), 1 DFMA.  Returns TFLOP/s in *tflops. */
+gogp_status gogp_debug_fp64_peak(gogp_handle* h, int which, double* tflops);
+
+/* One C -= A B^T of size n (tiles of the trailing update), timed; returns
+ * TFLOP/s.  mode 0 full, 1 lower-triangular (SYRK). */
+gogp_status gogp_debug_gemm(gogp_handle* h, int64_t n, int64_t k, int mode, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOGP_B200_H */

@@ -1,0 +1,269 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (via the ctypes
+host mirror gogp_b200.gp), against the reference's golden vectors and against the
+CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): relative 1e-9 on the LML (relative to
+max(|LML|, N)), 1e-7 on gradients and predictive moments
+(max-norm error over max(norm, 1))."""
+import numpy as np
+import pytest
+
+from tests import cases
+from tests.golden_ref import DX, ELEMENTAL, EPS, PRODUCE, arr
+
+pytestmark = pytest.mark.gpu
+
+LML_TOL, GRAD_TOL, PRED_TOL = 1e-9, 1e-7, 1e-7
+
+
+def _dev_noise(n):
+    from gogp_b200 import kernel as k
+    return k.UniformNoise if n == "uniform" else k.ConstantNoise(n)
+
+
+def _grad_err(g, ref):
+    return float(np.max(np.abs(g - ref)) / max(1.0, np.max(np.abs(ref)))) if len(ref) else 0.0
+
+
+# ---- the reference's own tables (gp/gp_test.go) through the C-ABI ---------------------
+@pytest.mark.parametrize("case", PRODUCE, ids=[c[0] for c in PRODUCE])
+def test_produce_goldens(case):
+    from gogp_b200 import GP, kernel as k
+    name, nstd, theta, x, y, z, mu, sigma = case
+    for parallel in (False, True):  # gp/gp_test.go:123-132
+        g = GP(NDim=1, Simil=k.Normal, Noise=k.ConstantNoise(nstd), ThetaSimil=theta)
+        g.Parallel = parallel
+        err = g.Absorb(x, y)
+        assert err is None, err
+        m, s, err = g.Produce(z)
+        assert err is None, err
+        assert len(m) == len(mu) and len(s) == len(sigma)
+        assert np.all(np.abs(m - arr(mu)) <= 1e-6), (m, mu)
+        assert np.all(np.abs(s - arr(sigma)) <= 1e-6), (s, sigma)
+
+
+@pytest.mark.parametrize("case", ELEMENTAL, ids=[c[0] for c in ELEMENTAL])
+def test_elemental_goldens(case):
+    from gogp_b200 import GP, kernel as k
+    name, n, x, ll = case
+    x = arr(x)
+    g = GP(NDim=1, Simil=k.Normal, Noise=_dev_noise(n))
+    v = g.Observe(x)
+    dll = g.Gradient()
+    assert abs(v - ll) < 1e-6
+    assert len(dll) == len(x)
+    for j in range(len(x)):  # forward difference, gp/gp_test.go:242-252
+        x0 = x[j]
+        x[j] += DX
+        vj = g.Observe(x)
+        x[j] = x0
+        assert abs(dll[j] - (vj - v) / DX) <= EPS, (j, dll[j], (vj - v) / DX)
+    P = g.Simil.NTheta() + g.Noise.NTheta()
+    v2 = g.Observe(x[:P].copy())  # hyper-parameters only, gp/gp_test.go:254-267
+    assert abs(v2 - ll) < 1e-6
+    assert len(g.Gradient()) == P
+
+
+# ---- covariance build / descriptor interpreter, element by element ---------------------
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_cov_build_matches_oracle(name):
+    import ctypes as C
+    from gogp_b200 import _lib
+    N = 200
+    X, y, logt = cases.synth(name, N, seed=5)
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    og.X, og.Y = X, y
+    og.observe(logt.copy())
+    nts = dg.Simil.NTheta()
+    th = np.exp(logt)
+    out = np.zeros((N, N))
+    Xf = np.ascontiguousarray(X).ravel()
+    ts, tn = np.ascontiguousarray(th[:nts]), np.ascontiguousarray(th[nts:])
+    st = _lib.lib().gogp_debug_build(dg._handle(), _lib.dptr(ts), _lib.dptr(tn), _lib.dptr(Xf), N, _lib.dptr(out))
+    assert st == _lib.OK
+    assert np.max(np.abs(out - og.K) / np.maximum(np.abs(og.K), 1e-300)) < 5e-14  # a few ulp of exp/sin
+    assert np.max(np.abs(out - og.K)) < 1e-14 * max(1.0, np.abs(og.K).max())
+
+
+# ---- LML + gradient + Produce against the oracle -----------------------------------------
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+@pytest.mark.parametrize("N", [1, 2, 37, 128, 129, 300])
+def test_hyper_only_parity(name, N):
+    X, y, logt = cases.synth(name, N, seed=N)
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    x = logt.copy()
+    lml = dg.Observe(x)
+    assert np.allclose(x, logt, rtol=0, atol=1e-15)  # exp/log round trip of the caller's slice
+    ref = og.observe(logt.copy())
+    assert abs(lml - ref) <= LML_TOL * max(abs(ref), N), (lml, ref)
+    g = dg.Gradient()
+    gref = og.gradient()
+    assert len(g) == len(gref) == len(logt)
+    assert _grad_err(g, gref) <= GRAD_TOL, (g, gref)
+    # Produce at in-sample, interpolated and far-away points
+    rng = np.random.default_rng(1000 + N)
+    Z = np.concatenate([X[:min(N, 5)], rng.uniform(X.min() - 1, X.max() + 1, size=(70, X.shape[1]))])
+    mu, sigma, err = dg.Produce(Z)
+    assert err is None
+    mref, sref = og.produce(Z, clamp=True)
+    assert np.max(np.abs(mu - mref)) <= PRED_TOL * max(1.0, np.abs(mref).max())
+    # sigma = sqrt(small difference): compare variances, where the rounding lives
+    assert np.max(np.abs(sigma ** 2 - sref ** 2)) <= PRED_TOL * max(1.0, np.abs(sref).max() ** 2)
+
+
+@pytest.mark.parametrize("name", ["normal_uniform", "anynoise", "warpedtime", "hyperpriors", "c3_ard3", "c5_matern4"])
+@pytest.mark.parametrize("N", [1, 3, 43, 150])
+def test_with_obs_parity(name, N):
+    """Observe's [theta | X | Y] layout: gradient w.r.t. inputs and outputs too
+    (tutorial anynoise optimises Y, warpedtime optimises X)."""
+    X, y, logt = cases.synth(name, N, seed=7 * N)
+    x = np.concatenate([logt, X.ravel(), y])
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    lml = dg.Observe(x.copy())
+    ref = og.observe(x.copy())
+    assert abs(lml - ref) <= LML_TOL * max(abs(ref), N)
+    g = dg.Gradient()
+    gref = og.gradient()
+    assert len(g) == len(x)
+    assert _grad_err(g, gref) <= GRAD_TOL, np.max(np.abs(g - gref))
+
+
+def test_barebones_kat():
+    """Config 1 (tutorial/barebones on tutorial/data), SURVEY.md section 8(c)."""
+    from oracle.gp import mean_std
+    d = np.loadtxt(cases.GOLDEN + "/barebones.csv", delimiter=",")
+    m, s = mean_std(d[:, 1])
+    g = cases.make_device_gp("barebones")
+    g.X, g.Y = d[:, :1].copy(), (d[:, 1] - m) / s
+    assert abs(g.Observe(np.zeros(3)) - (-8.482987052156)) < 1e-9
+    assert np.allclose(g.Gradient(), [-3.2320901320, 6.9054771170, -0.4752473692], atol=1e-8)
+    assert abs(g.Observe(arr([-0.5, 0.3, 1.0])) - (-9.103987864150)) < 1e-9
+    assert np.allclose(g.Gradient(), [-0.1009289296, 2.3769085404, -7.5447626235], atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["barebones", "hyperpriors", "anynoise", "warpedtime"])
+def test_tutorial_expanding_window(name):
+    """tutorial.Evaluate's loop shape (tutorial/tutorial.go:91-179): N = 0..len-1 on the
+    shipped data, one Observe+Gradient and a one-step forecast per prefix."""
+    from oracle.gp import mean_std
+    d = np.loadtxt(cases.GOLDEN + "/%s.csv" % name, delimiter=",")
+    m, s = mean_std(d[:, 1])
+    X, Y = d[:, :1].copy(), (d[:, 1] - m) / s
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    P = dg.Simil.NTheta() + dg.Noise.NTheta()
+    logt = np.zeros(P)
+    for end in range(0, len(X), 3):
+        dg.X, dg.Y = X[:end], Y[:end]
+        og.X, og.Y = X[:end], Y[:end]
+        lml = dg.Observe(logt.copy())
+        ref = og.observe(logt.copy())
+        assert abs(lml - ref) <= LML_TOL * max(abs(ref), end, 1)
+        assert _grad_err(dg.Gradient(), og.gradient()) <= GRAD_TOL
+        mu, sigma, err = dg.Produce(X[end:end + 1])
+        mref, sref = og.produce(X[end:end + 1], clamp=True)
+        assert err is None
+        assert abs(mu[0] - mref[0]) <= PRED_TOL * max(1.0, abs(mref[0]))
+        assert abs(sigma[0] ** 2 - sref[0] ** 2) <= PRED_TOL
+
+
+# ---- error behaviour -------------------------------------------------------------------------
+def test_not_positive_definite_panics_in_observe_and_errors_in_absorb():
+    from gogp_b200 import GP, GoGPPanic, _lib, kernel as k
+    g = GP(NDim=1, Simil=k.Normal, Noise=k.ConstantNoise(0.0), ThetaSimil=[1.0])
+    err = g.Absorb([[0.0], [0.0]], [1.0, 2.0])  # duplicate input, zero noise: singular K
+    assert err is not None and err.status == _lib.NOT_POSITIVE_DEFINITE
+    with pytest.raises(GoGPPanic):
+        g.Observe(arr([0.0, 0.0, 0.0, 1.0, 2.0]))
+
+
+def test_bad_length_panics():
+    from gogp_b200 import GoGPPanic
+    g = cases.make_device_gp("c5_matern4")
+    with pytest.raises(GoGPPanic):
+        g.Observe(np.zeros(5 + 1 + 7))  # 7 is not a multiple of NDim+1 = 5
+
+
+def test_default_noise_is_1e_5():
+    """Noise == nil -> ConstantNoise(1e-5), gp/gp.go:43-48."""
+    from gogp_b200 import GP, kernel as k
+    from oracle import kernels as ok
+    from oracle.gp import GP as OGP
+    X, y, _ = cases.synth("normal_const", 12, seed=2, spread=30.0)
+    g = GP(NDim=1, Simil=k.Normal)
+    o = OGP(1, ok.Normal)
+    g.X, g.Y = X, y
+    o.X, o.Y = X, y
+    ref = o.observe(np.zeros(1))
+    assert abs(g.Observe(np.zeros(1)) - ref) <= 1e-7 * max(abs(ref), 12)  # cond(K) is large here
+
+
+# ---- mid-size differential + size-independent properties --------------------------------------
+@pytest.mark.parametrize("name,N", [("c2_rbf", 1000), ("c3_ard8", 1500), ("c5_matern4", 2048), ("hyperpriors", 1100)])
+def test_midsize_parity(name, N):
+    X, y, logt = cases.synth(name, N, seed=N)
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    lml = dg.Observe(logt.copy())
+    ref = og.observe(logt.copy())
+    assert abs(lml - ref) <= LML_TOL * max(abs(ref), N), (lml, ref)
+    g, gref = dg.Gradient(), og.gradient()
+    assert _grad_err(g, gref) <= GRAD_TOL, (g, gref)
+    Z = np.random.default_rng(1).uniform(X.min(), X.max(), size=(300, X.shape[1]))
+    mu, sigma, err = dg.Produce(Z)
+    mref, sref = og.produce(Z, clamp=True)
+    assert err is None
+    assert np.max(np.abs(mu - mref)) <= PRED_TOL * max(1.0, np.abs(mref).max())
+    assert np.max(np.abs(sigma ** 2 - sref ** 2)) <= PRED_TOL * max(1.0, np.abs(sref).max() ** 2)
+
+
+def test_factor_and_inverse_residuals_4096():
+    """C2 size (N = 4096): residuals ||L L^T - K|| / ||K||, ||K K^-1 - I||, ||K alpha - y|| / ||y||
+    computed on the host from the fetched device state."""
+    import ctypes as C
+    from gogp_b200 import _lib
+    N = 4096
+    X, y, logt = cases.synth("c2_rbf", N, seed=0)
+    dg = cases.make_device_gp("c2_rbf")
+    og = cases.make_oracle_gp("c2_rbf")
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    lml = dg.Observe(logt.copy())
+    ref = og.observe(logt.copy())
+    assert abs(lml - ref) <= LML_TOL * max(abs(ref), N)
+    Lm = np.zeros((N, N))
+    assert _lib.lib().gogp_get_factor(dg._handle(), _lib.dptr(Lm), N) == _lib.OK
+    K = og.K
+    assert np.linalg.norm(Lm @ Lm.T - K) / np.linalg.norm(K) < 1e-13
+    alpha = dg.Alpha()
+    assert np.linalg.norm(K @ alpha - y) / np.linalg.norm(y) < 1e-9
+    g, gref = dg.Gradient(), og.gradient()
+    assert _grad_err(g, gref) <= GRAD_TOL
+    Kinv = np.zeros((N, N))
+    assert _lib.lib().gogp_debug_fetch(dg._handle(), 2, _lib.dptr(Kinv), N) == _lib.OK
+    assert np.linalg.norm(K @ Kinv - np.eye(N)) / np.sqrt(N) < 1e-9
+    Z = np.random.default_rng(3).uniform(X.min(), X.max(), size=(1024, 1))
+    mu, sigma, err = dg.Produce(Z)
+    mref, sref = og.produce(Z, clamp=True)
+    assert np.max(np.abs(mu - mref)) <= PRED_TOL * max(1.0, np.abs(mref).max())
+    assert np.max(np.abs(sigma ** 2 - sref ** 2)) <= PRED_TOL
+
+
+def test_repeatable_and_handle_reuse():
+    """Same inputs -> bit-identical results (fixed reduction orders); a handle survives
+    growing and shrinking N."""
+    dg = cases.make_device_gp("c3_ard3")
+    res = []
+    for N in (300, 50, 700, 300):
+        X, y, logt = cases.synth("c3_ard3", N, seed=1)
+        dg.X, dg.Y = X, y
+        res.append((dg.Observe(logt.copy()), dg.Gradient()))
+    assert res[0][0] == res[3][0]
+    assert np.array_equal(res[0][1], res[3][1])
