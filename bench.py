@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Headline benchmark: LML + hyper-parameter-gradient evaluations per second at
+N = 32768, FP64 (BASELINE.json metric; workload = configs[2]: synthetic 8-D scaled
+Normal x Periodic + noise, hyper-parameters-only Observe followed by Gradient).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" is one evaluation: gp.GP.Observe(theta) + gp.GP.Gradient() at a fresh
+theta (covariance build, Cholesky, solves, K^-1, fused gradient trace).  With N > 1
+GPUs (torchrun, one rank per GPU) every rank evaluates its own restart's theta on
+the same data -- the multi-start sharding of north_star: no data-path collective,
+weak scaling, value = evaluations of all ranks / max-over-ranks device time.
+
+`value`  : inputs (X, Y) resident in HBM, device time (CUDA events on the handle's stream).
+`e2e`    : the same evaluations through the C-ABI with HOST buffers: X, Y and theta
+           are copied from pinned host memory every step, LML and gradient come back.
+`--impl reference`: the reference's CPU algorithm (oracle port, literal gp/gp.go
+           mode: materialised dK, per-parameter GEMM + Cholesky solve + trace) on the
+           host cores, on a bounded sample size, extrapolated by its N^3 cost law.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LML+grad evals/sec at N=32768 fp64"
+UNIT = "evals/s"
+WORKLOAD = "configs[2]: synthetic 8-D scaled Normal x Periodic + noise, N=32768, hyper-parameters-only Observe+Gradient"
+N_FULL, NDIM = 32768, 8
+NOMINAL_FP64_TFLOPS = 148 * 128 * 1.965e9 / 1e12  # 64 FP64 FMA/clk/SM at clocks.max.sm
+
+
+def synth(N, seed=0):
+    """x ~ U(0,4)^8, y = sum_d sin(x_d) + 0.1 N(0,1) normalised;
+    truth theta0 = 1, l_d = 1, l_p = 1, p = 2, sigma = 0.1 (noise variance 1e-2)."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0.0, 4.0, size=(N, NDIM))
+    y = np.sin(X).sum(axis=1) + 0.1 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    truth = np.zeros(NDIM + 4)
+    truth[NDIM + 2] = np.log(2.0)   # period
+    truth[NDIM + 3] = np.log(0.1)   # noise std
+    return X, y, truth
+
+
+def theta_for(truth, rank, step):
+    """A fresh point per (restart, step): truth + 0.1 N(0,1), like the jittered starts of
+    tutorial/tutorial.go:119-121; deterministic."""
+    rng = np.random.default_rng(1000003 * (rank + 1) + step)
+    return truth + 0.1 * rng.standard_normal(len(truth))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_eval(N_s, mode, truth):
+    """One Observe+Gradient of the oracle port on the host (TEST INFRASTRUCTURE used as the
+    timed CPU baseline, never as the product path)."""
+    from oracle.gp import GP as OGP
+    from oracle import kernels as ok
+    X, y, _ = synth(N_s, seed=1)
+    g = OGP(NDIM, ok.ArdNormalTimesPeriodic(NDIM), ok.UniformNoise)
+    g.X, g.Y = X, y
+    th = theta_for(truth, 0, 0)
+    t0 = time.perf_counter()
+    g.observe(th.copy())
+    g.gradient(mode)
+    total = time.perf_counter() - t0
+    # O(N^2) element work and O(N^3) dense algebra are extrapolated by their own laws
+    elem = g.t_elem
+    return total, elem, total - elem
+
+
+def extrapolate(total, elem, dense, N_s, N):
+    r = N / N_s
+    return elem * r ** 2 + dense * r ** 3
+
+
+def run_reference(args, rank):
+    """bench.py --impl reference: the reference's CPU implementation of the path."""
+    if rank != 0:
+        return
+    N = args.n
+    N_s = min(N, args.cpu_sample_n)
+    _, _, truth = synth(8, 0)
+    for _ in range(args.warmup):
+        if N_s > 1024:
+            break  # a warm-up step costs as much as a timed one; BLAS threads need no warming
+        cpu_port_eval(N_s, "literal", truth)
+    runs = [cpu_port_eval(N_s, "literal", truth) for _ in range(args.steps)]
+    t = float(np.mean([r[0] for r in runs]))
+    t_full = float(np.mean([extrapolate(*r, N_s, N) for r in runs]))
+    scale = t_full / t
+    value = 1.0 / t_full
+    cores = os.cpu_count()
+    sample = ("oracle port of gp/gp.go in literal mode (materialised dK, per-parameter GEMM + Cholesky solve + trace) "
+              "on NumPy/OpenBLAS -- not gonum, not Go; timed at N=%d (%.2f s/evaluation), EXTRAPOLATED to N=%d: "
+              "element work x (N/N_s)^2, dense algebra x (N/N_s)^3 (the literal algorithm needs (P+5) N^2 8 B = "
+              "146 GB at N=32768 and cannot run there)" % (N_s, t, N))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * scale, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "N": N, "ndim": NDIM, "ntheta": NDIM + 4, "sample_N": N_s,
+                   "measured_ms_per_sample_step": t * 1e3, "extrapolated": N_s != N},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_FULL, help="observations (default: the metric's N=32768)")
+    ap.add_argument("--cpu-sample-n", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from gogp_b200 import _lib
+    from gogp_b200 import kernel as k
+
+    def ard_normal_periodic(D):
+        # theta0 * prod_d Normal(l_d; dim d) * Periodic(l_p, p; dim 0)   
+        e = k.Param(0)
+        for d in range(D):
+            e = e * k.Normal.Of(l=1 + d, dim=d)
+        return e * k.Periodic.Of(l=1 + D, p=2 + D, dim=0)
+
+    L = _lib.lib()
+    N = args.n
+    P = NDIM + 4
+    X, y, truth = synth(N, seed=0)
+
+    simil, noise = ard_normal_periodic(NDIM), k.UniformNoise
+    sd, nd = simil.Descriptor(), noise.Descriptor()
+    h = C.c_void_p()
+
+    def ck(st):
+        if st != _lib.OK:
+            raise SystemExit("gogp error %d: %s" % (st, L.gogp_last_error(h).decode()))
+
+    ck(L.gogp_create(NDIM, sd, len(sd), simil.NTheta(), nd, len(nd), noise.NTheta(), local_rank, C.byref(h)))
+
+    # pinned host buffers (the e2e leg copies from these every step)
+    Xp = torch.from_numpy(X.reshape(-1).copy()).pin_memory()
+    Yp = torch.from_numpy(y.copy()).pin_memory()
+    Tp = torch.zeros(P, dtype=torch.float64).pin_memory()
+    Gp = torch.zeros(P, dtype=torch.float64).pin_memory()
+    dp = C.POINTER(C.c_double)
+    xptr, yptr = C.cast(Xp.data_ptr(), dp), C.cast(Yp.data_ptr(), dp)
+    tptr, gptr = C.cast(Tp.data_ptr(), dp), C.cast(Gp.data_ptr(), dp)
+    lml = C.c_double()
+
+    def step_resident(i):
+        Tp.numpy()[:] = theta_for(truth, rank, i)
+        ck(L.gogp_observe(h, tptr, 0, None, None, 0, C.byref(lml)))
+        ck(L.gogp_gradient(h, gptr, P))
+
+    def step_e2e(i):
+        Tp.numpy()[:] = theta_for(truth, rank, i)
+        ck(L.gogp_observe(h, tptr, 0, xptr, yptr, N, C.byref(lml)))
+        ck(L.gogp_gradient(h, gptr, P))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ck(L.gogp_set_data(h, xptr, yptr, N))
+    for i in range(args.warmup):
+        step_resident(-1 - i)
+
+    # ---- timed region: inputs resident in HBM ----------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    launches0 = L.gogp_launch_count(h)
+    ms = C.c_double()
+    ck(L.gogp_timer_start(h))
+    phases = np.zeros(len(_lib.PHASES))
+    ph = np.zeros(len(_lib.PHASES))
+    for i in range(args.steps):
+        step_resident(i)
+        L.gogp_phase_times(h, _lib.dptr(ph))
+        phases += ph
+    ck(L.gogp_timer_stop(h, C.byref(ms)))
+    sync_all()
+    launches = L.gogp_launch_count(h) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = max_over_ranks(ms.value)
+    value = world * args.steps / (t_ms * 1e-3)
+    phases /= args.steps
+    last_lml, last_grad = lml.value, Gp.numpy().copy()
+
+    # ---- e2e: host buffers through the C-ABI every step ---------------------------------
+    step_e2e(-100)
+    sync_all()
+    ck(L.gogp_timer_start(h))
+    w0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    ck(L.gogp_timer_stop(h, C.byref(ms)))
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    sync_all()
+    e2e_ms = max_over_ranks(max(ms.value, wall_ms))
+    e2e_value = world * args.steps / (e2e_ms * 1e-3)
+    same = (lml.value == last_lml) and np.array_equal(Gp.numpy(), last_grad)
+
+    # ---- dominant kernel (DMMA GEMM): per-launch accounting in one extra step -----------
+    gemm_ms, gemm_flops, gemm_n = C.c_double(), C.c_double(), C.c_int64()
+    ck(L.gogp_profile_enable(h, 1))
+    step_resident(0)
+    ck(L.gogp_profile_read(h, C.byref(gemm_ms), C.byref(gemm_flops), C.byref(gemm_n)))
+    ck(L.gogp_profile_enable(h, 0))
+    peak_dmma, peak_dfma = C.c_double(), C.c_double()
+    ck(L.gogp_debug_fp64_peak(h, 0, C.byref(peak_dmma)))
+    ck(L.gogp_debug_fp64_peak(h, 1, C.byref(peak_dfma)))
+    L.gogp_destroy(h)
+
+    if rank == 0:
+        alg_flops = float(N) ** 3  # LML+gradient evaluation = N^3 flop
+        achieved = alg_flops / (gemm_ms.value * 1e-3) / 1e12
+        peak = peak_dmma.value
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "N": N, "ndim": NDIM, "ntheta": P,
+                       "parallelism": "restart-sharded x%d (one restart per GPU, no collective)" % world,
+                       "l2": "inputs larger than L2 (K, L, K^-1 are %.1f GB each; L2 is 126 MB)" % (8.0 * N * N / 1e9)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (N * NDIM + N + P),
+                    "d2h_bytes_per_step": 8 * (1 + P), "ms_per_step": e2e_ms / args.steps,
+                    "bit_identical_to_resident": bool(same)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "phases_ms": dict(zip(_lib.PHASES, [round(float(v), 3) for v in phases])),
+            "cholesky_tflops": float(N) ** 3 / 3 / (phases[2] * 1e-3) / 1e12 if phases[2] > 0 else None,
+            "potri_tflops": 2 * float(N) ** 3 / 3 / (phases[4] * 1e-3) / 1e12 if phases[4] > 0 else None,
+            "roofline": {
+                "bound": "tensor", "kernel": "dgemm_nt_kernel (DMMA.8x8x4)", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": "measured in this run: mma.sync.m8n8k4.f64 register-only issue-rate microbenchmark "
+                               "(MEASURED_PEAKS.json has no FP64 entry); DFMA microbenchmark %.2f TFLOP/s; nominal "
+                               "%.1f TFLOP/s = 148 SM x 64 FMA/clk x 1965 MHz" % (peak_dfma.value, NOMINAL_FP64_TFLOPS),
+                "algorithmic_flops_per_step": alg_flops, "executed_flops_per_step": gemm_flops.value,
+                "launches_per_step": int(gemm_n.value), "kernel_ms_per_step": gemm_ms.value,
+                "share_of_step": gemm_ms.value / (t_ms / args.steps),
+                "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
+            },
+            "lml": last_lml,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            N_s = min(N, args.cpu_sample_n)
+            lit = cpu_port_eval(N_s, "literal", truth)
+            N_f = min(N, 2 * args.cpu_sample_n)
+            fast = cpu_port_eval(N_f, "fast", truth)
+            out["cpu_baseline"] = {
+                "value": 1.0 / extrapolate(*lit, N_s, N), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": "oracle port of gp/gp.go, literal mode (per-parameter GEMM + Cholesky solve + trace), "
+                          "NumPy/OpenBLAS, one evaluation at N=%d took %.2f s (%.2f s element work, %.2f s dense "
+                          "algebra); EXTRAPOLATED to N=%d: element work x (N/N_s)^2, dense algebra x (N/N_s)^3"
+                          % (N_s, lit[0], lit[1], lit[2], N),
+                "fast_algorithm": {"value": 1.0 / extrapolate(*fast, N_f, N), "unit": UNIT,
+                                   "sample": "same maths in its efficient CPU form (dpotrf + K^-1 + elementwise "
+                                             "trace), one evaluation at N=%d took %.2f s; extrapolated the same way"
+                                             % (N_f, fast[0])},
+            }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

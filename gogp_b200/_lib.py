@@ -25,7 +25,7 @@ SYMBOLS = (
     "gogp_create", "gogp_destroy", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_lml",
     "gogp_produce", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
-    "gogp_debug_gemm",
+    "gogp_debug_gemm", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
 )
 
 
@@ -91,6 +91,14 @@ def lib():
     L.gogp_debug_fp64_peak.restype = C.c_int
     L.gogp_debug_gemm.argtypes = [H, C.c_int64, C.c_int64, C.c_int, C.c_int, dp]
     L.gogp_debug_gemm.restype = C.c_int
+    L.gogp_timer_start.argtypes = [H]
+    L.gogp_timer_start.restype = C.c_int
+    L.gogp_timer_stop.argtypes = [H, dp]
+    L.gogp_timer_stop.restype = C.c_int
+    L.gogp_profile_enable.argtypes = [H, C.c_int]
+    L.gogp_profile_enable.restype = C.c_int
+    L.gogp_profile_read.argtypes = [H, dp, dp, C.POINTER(C.c_int64)]
+    L.gogp_profile_read.restype = C.c_int
     _lib = L
     return L
 

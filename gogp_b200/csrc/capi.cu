@@ -22,13 +22,54 @@ constexpr int64_t kProduceChunk = 8192;
 
 inline int64_t pad_tile(int64_t n) { return n <= 0 ? 0 : ((n + TILE - 1) / TILE) * TILE; }
 
+// Per-launch accounting of the GEMM (gogp_profile_enable).
+struct GemmProfile {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;  // pairs
+    size_t used = 0;
+    double flops = 0.0;
+    int64_t launches = 0;
+    cudaEvent_t next() {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+        }
+        return ev[used++];
+    }
+};
+
+inline double gemm_flops(int64_t m, int64_t n, int64_t k, int mode) {
+    const double tm = (double)(m / TILE), tn = (double)(n / TILE), tk = (double)(k / TILE);
+    const double per = 2.0 * TILE * TILE * TILE;  // one 128^3 tile step
+    double steps = 0.0;
+    if (mode & GEMM_KTRI) {
+        // tile row ti runs k tiles ti..tk-1
+        for (int64_t ti = 0; ti < m / TILE; ++ti) {
+            const double cols = (mode & GEMM_LOWER) ? (double)(ti + 1) : tn;
+            steps += cols * (tk - (double)ti);
+        }
+    } else {
+        steps = ((mode & GEMM_LOWER) ? tm * (tm + 1) / 2 : tm * tn) * tk;
+    }
+    return steps * per;
+}
+
 struct CudaBackend {
     cudaStream_t s;
     int* info;
     int64_t* launches;
+    GemmProfile* prof;
     void gemm(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m, int64_t n,
               int64_t k, double alpha, double beta, int mode, double* cdiag) {
+        const bool p = prof && prof->on;
+        if (p) cudaEventRecord(prof->next(), s);
         launch_dgemm_nt(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s);
+        if (p) {
+            cudaEventRecord(prof->next(), s);
+            prof->flops += gemm_flops(m, n, k, mode);
+            ++prof->launches;
+        }
         ++*launches;
     }
     void potrf_leaf(double* A, int64_t ld, double* winv, int base) {
@@ -71,8 +112,9 @@ struct gogp_handle {
     double lml = 0.0;
     std::string err;
     double phase_ms[GOGP_NPHASE] = {0};
-    cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t ev[10] = {nullptr};
     int64_t launches = 0;
+    GemmProfile prof;
 };
 
 namespace {
@@ -191,7 +233,7 @@ gogp_status absorb(gogp_handle* h) {
     ++h->launches;
     CK(cudaEventRecord(h->ev[1], s));
 
-    CudaBackend be{s, h->dInfo, &h->launches};
+    CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
     Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
     bl.potrf(0, Npad);
     CK(cudaEventRecord(h->ev[2], s));
@@ -287,6 +329,7 @@ void gogp_destroy(gogp_handle* h) {
     if (h->hPin) cudaFreeHost(h->hPin);
     for (auto& ev : h->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->prof.ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -319,9 +362,11 @@ gogp_status gogp_observe(gogp_handle* h, const double* log_theta, int with_obs, 
     h->with_obs = with_obs != 0;
     gogp_status st = absorb(h);
     if (st != GOGP_OK) return st;
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
-    h->phase_ms[GOGP_PHASE_UPLOAD] = ms;
+    if (h->N > 0) {  // events are complete: absorb synchronised the stream
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+        h->phase_ms[GOGP_PHASE_UPLOAD] = ms;
+    }
     *lml = h->lml;
     return GOGP_OK;
 }
@@ -368,7 +413,7 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
 
     CK(cudaEventRecord(h->ev[0], s));
     if (!h->have_kinv) {
-        CudaBackend be{s, h->dInfo, &h->launches};
+        CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
         Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
         bl.trtri_t(h->dB, 0, Npad);
         bl.lauum(h->dB, h->dDg, Npad);
@@ -454,7 +499,7 @@ gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu,
         if (N > 0) {
             launch_cov_cross(prog, h->dXt, N, Npad, h->dZt, mc, mpad, D, h->dBt, s);
             launch_row_reduce(h->dBt, Npad, mc, Npad, h->dAlpha, dmu, s);  // mean = Kstar^T alpha, gp/gp.go:335
-            CudaBackend be{s, h->dInfo, &h->launches};
+            CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
             Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
             bl.trsm(h->dBt, Npad, mpad, 0, Npad);                        // V^T = Kstar^T L^-T
             launch_row_reduce(h->dBt, Npad, mc, Npad, nullptr, dss, s);  // diag(Kstar^T K^-1 Kstar)
@@ -546,20 +591,22 @@ gogp_status gogp_debug_fp64_peak(gogp_handle* h, int which, double* tflops) {
     CK(cudaSetDevice(h->dev));
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev));
-    const int iters = 20000;
-    launch_fp64_peak(which, 1000, h->dRed + 32, h->stream);  // warm-up
     double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
-        CK(cudaEventRecord(h->ev[0], h->stream));
-        launch_fp64_peak(which, iters, h->dRed + 32, h->stream);
-        CK(cudaEventRecord(h->ev[1], h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-        double tf = fp64_peak_flops_per_launch(which, iters, nsm) / (ms * 1e-3) / 1e12;
-        if (tf > best) best = tf;
+    for (int v = 0; v < fp64_peak_variants(); ++v) {
+        const int iters = 4000;
+        launch_fp64_peak(which, v, 200, h->dRed + 32, h->stream);  // warm-up
+        for (int rep = 0; rep < 3; ++rep) {
+            CK(cudaEventRecord(h->ev[0], h->stream));
+            launch_fp64_peak(which, v, iters, h->dRed + 32, h->stream);
+            CK(cudaEventRecord(h->ev[1], h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+            double tf = fp64_peak_flops_per_launch(which, v, iters, nsm) / (ms * 1e-3) / 1e12;
+            if (tf > best) best = tf;
+        }
+        h->launches += 4;
     }
-    h->launches += 6;
     CK(cudaGetLastError());
     *tflops = best;
     return GOGP_OK;
@@ -590,6 +637,51 @@ gogp_status gogp_debug_gemm(gogp_handle* h, int64_t n, int64_t k, int mode, int 
     const double tiles = mode ? T * (T + 1) / 2 : T * T;
     const double flops = tiles * 2.0 * TILE * TILE * (double)k * iters;
     *tflops = flops / (ms * 1e-3) / 1e12;
+    return GOGP_OK;
+}
+
+gogp_status gogp_timer_start(gogp_handle* h) {
+    if (!h) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    CK(cudaEventRecord(h->ev[8], h->stream));
+    return GOGP_OK;
+}
+
+gogp_status gogp_timer_stop(gogp_handle* h, double* ms) {
+    if (!h || !ms) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    CK(cudaEventRecord(h->ev[9], h->stream));
+    CK(cudaEventSynchronize(h->ev[9]));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, h->ev[8], h->ev[9]));
+    *ms = f;
+    return GOGP_OK;
+}
+
+gogp_status gogp_profile_enable(gogp_handle* h, int on) {
+    if (!h) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    CK(cudaStreamSynchronize(h->stream));
+    h->prof.on = on != 0;
+    h->prof.used = 0;
+    h->prof.flops = 0.0;
+    h->prof.launches = 0;
+    return GOGP_OK;
+}
+
+gogp_status gogp_profile_read(gogp_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+    if (!h || !gemm_ms || !gemm_flops || !gemm_launches) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    CK(cudaStreamSynchronize(h->stream));
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < h->prof.used; i += 2) {
+        float f = 0.f;
+        CK(cudaEventElapsedTime(&f, h->prof.ev[i], h->prof.ev[i + 1]));
+        total += f;
+    }
+    *gemm_ms = total;
+    *gemm_flops = h->prof.flops;
+    *gemm_launches = h->prof.launches;
     return GOGP_OK;
 }
 

@@ -153,46 +153,48 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(const GemmArgs g) {
 }
 
 // ---- FP64 peak microbenchmarks (registers only) --------------------------------------
+template <int NACC>
 __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {
-    double c[16][2];
+    double c[NACC][2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    for (int i = 0; i < NACC; ++i) c[i][0] = c[i][1] = 0.0;
     double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dmma(c[i][0], c[i][1], a, b);
+        for (int i = 0; i < NACC; ++i) dmma(c[i][0], c[i][1], a, b);
     }
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
     if (s == 123.456) sink[0] = s;
 }
 
+template <int NACC>
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* sink) {
-    double c[16];
+    double c[NACC];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-9 + i;
+    for (int i = 0; i < NACC; ++i) c[i] = threadIdx.x * 1e-9 + i;
     double a = 1.0 + threadIdx.x * 1e-12, b = 1e-9;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+        for (int i = 0; i < NACC; ++i) c[i] = fma(c[i], a, b);
     }
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += c[i];
+    for (int i = 0; i < NACC; ++i) s += c[i];
     if (s == 123.456) sink[0] = s;
 }
-
-constexpr int PEAK_CTAS_PER_SM = 4;
 
 }  // namespace
 
 void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};  // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-        configured = true;
+        configured[dev & 63] = true;
     }
     GemmArgs g;
     g.C = C;
@@ -213,20 +215,32 @@ void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const
     dgemm_nt_kernel<<<ntiles, 256, GEMM_SMEM, s>>>(g);
 }
 
-void launch_fp64_peak(int which, int iters, double* sink, cudaStream_t s) {
+// variant = nacc_index * 4 + ctas_index; nacc in {8, 16, 32}, CTAs per SM in {1, 2, 4, 8}
+static const int kPeakAcc[3] = {8, 16, 32};
+static const int kPeakCtas[4] = {1, 2, 4, 8};
+int fp64_peak_variants() { return 12; }
+
+void launch_fp64_peak(int which, int variant, int iters, double* sink, cudaStream_t s) {
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (which == 0)
-        dmma_peak_kernel<<<nsm * PEAK_CTAS_PER_SM, 256, 0, s>>>(iters, sink);
-    else
-        dfma_peak_kernel<<<nsm * PEAK_CTAS_PER_SM, 256, 0, s>>>(iters, sink);
+    const int ai = variant / 4, grid = nsm * kPeakCtas[variant % 4];
+    if (which == 0) {
+        if (ai == 0) dmma_peak_kernel<8><<<grid, 256, 0, s>>>(iters, sink);
+        if (ai == 1) dmma_peak_kernel<16><<<grid, 256, 0, s>>>(iters, sink);
+        if (ai == 2) dmma_peak_kernel<32><<<grid, 256, 0, s>>>(iters, sink);
+    } else {
+        if (ai == 0) dfma_peak_kernel<8><<<grid, 256, 0, s>>>(iters, sink);
+        if (ai == 1) dfma_peak_kernel<16><<<grid, 256, 0, s>>>(iters, sink);
+        if (ai == 2) dfma_peak_kernel<32><<<grid, 256, 0, s>>>(iters, sink);
+    }
 }
 
-double fp64_peak_flops_per_launch(int which, int iters, int nsm) {
-    const double warps = (double)nsm * PEAK_CTAS_PER_SM * 8;
-    if (which == 0) return warps * iters * 16.0 * (8 * 8 * 4 * 2);  // DMMA m8n8k4
-    return warps * 32.0 * iters * 16.0 * 2;                       // DFMA
+double fp64_peak_flops_per_launch(int which, int variant, int iters, int nsm) {
+    const double warps = (double)nsm * kPeakCtas[variant % 4] * 8;
+    const double nacc = kPeakAcc[variant / 4];
+    if (which == 0) return warps * iters * nacc * (8 * 8 * 4 * 2);  // DMMA m8n8k4
+    return warps * 32.0 * iters * nacc * 2;                        // DFMA
 }
 
 }  // namespace gogp

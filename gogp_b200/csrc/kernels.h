@@ -45,8 +45,10 @@ enum GemmMode : int {
 // C[i][j] = beta*C[i][j] + alpha * sum_k A[i][k] B[j][k]; all of m, n, k multiples of 128.
 void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s);
-void launch_fp64_peak(int which, int iters, double* sink, cudaStream_t s);  // microbenchmark kernels
-double fp64_peak_flops_per_launch(int which, int iters, int nsm);
+// register-only issue-rate microbenchmarks: which = 0 DMMA m8n8k4, 1 DFMA
+int fp64_peak_variants();
+void launch_fp64_peak(int which, int variant, int iters, double* sink, cudaStream_t s);
+double fp64_peak_flops_per_launch(int which, int variant, int iters, int nsm);
 
 // ---- leaf.cu -------------------------------------------------------------------
 // Cholesky of the 128x128 diagonal tile at A (ld), in place (lower; upper zeroed),

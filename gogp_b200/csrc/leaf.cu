@@ -221,11 +221,13 @@ void launch_fill_pattern(double* v, int64_t n, cudaStream_t s) {
 }
 
 void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s) {
-    static bool configured = false;
     const size_t smem = (size_t)TILE * LP * sizeof(double);
-    if (!configured) {
+    static bool configured[64] = {false};  // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        configured[dev & 63] = true;
     }
     potrf_leaf_kernel<<<1, 512, smem, s>>>(A, ld, winv, info, base);
 }

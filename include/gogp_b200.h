@@ -147,6 +147,21 @@ gogp_status gogp_phase_times(const gogp_handle* h, double* ms /* GOGP_NPHASE */)
  * creation (bench.py's gpu_launches). */
 int64_t gogp_launch_count(const gogp_handle* h);
 
+/* Device-side stopwatch on the handle's stream (CUDA events): start records an
+ * event after all work queued so far, stop records another, waits for it and
+ * returns the milliseconds in between.  bench.py brackets its timed region with
+ * these because the handle's stream is not torch's current stream. */
+gogp_status gogp_timer_start(gogp_handle* h);
+gogp_status gogp_timer_stop(gogp_handle* h, double* ms);
+
+/* Per-launch accounting of the dominant kernel (the DMMA GEMM): while enabled,
+ * every GEMM launch is bracketed by CUDA events.  gogp_profile_read waits for the
+ * stream and returns, since the last enable, the summed device time of the GEMM
+ * launches, the FP64 flops they executed (2*128*128*k per tile, triangular k
+ * ranges counted as executed) and their number. */
+gogp_status gogp_profile_enable(gogp_handle* h, int on);
+gogp_status gogp_profile_read(gogp_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+
 /* Test/diagnostic access to device state: what = 0 K (before factorisation is
  * not kept; returns the factor buffer), 1 L, 2 K^-1 (after gogp_gradient).
  * out is N x N row-major, lower triangle valid, upper mirrored. */

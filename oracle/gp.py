@@ -13,6 +13,7 @@ gonum's Cholesky is replaced by LAPACK dpotrf/dpotrs through scipy: a different
 summation order in the same precision (see SURVEY.md section 7 "hard parts").
 """
 import math
+import time
 
 import numpy as np
 import scipy.linalg as sla
@@ -90,6 +91,10 @@ class GP:
         self.Alpha = None
         self.dK = None
         self.K = None
+        # wall-clock split used by bench.py's CPU baseline: O(N^2) element work
+        # (kernel evaluation, dK assembly, elementwise sums) vs O(N^3) dense algebra
+        self.t_elem = 0.0
+        self.t_dense = 0.0
 
     # gp/gp.go:45-57
     def _defaults(self):
@@ -118,6 +123,7 @@ class GP:
         if N == 0:
             return
         want = "none" if not with_grad else ("all" if self.with_obs else "theta")
+        t0 = time.perf_counter()
         k, kg = _pairs(self.Simil, self.ThetaSimil, self.X, self.X, want)
         n, ng = _noise(self.Noise, self.ThetaNoise, self.X, want)
         K = _sym_from_upper(k)
@@ -126,11 +132,14 @@ class GP:
         if with_grad:
             # chain rule for the log-parameters, gp/gp.go:114-116,138-140
             self._parts = dict(kg=kg, ng=ng)
+        t1 = time.perf_counter()
+        self.t_elem += t1 - t0
         try:
             self.L = sla.cholesky(K, lower=True, check_finite=False)
         except np.linalg.LinAlgError as e:  # gp/gp.go:228-230
             raise NotPositiveDefinite(str(e))
         self.Alpha = sla.cho_solve((self.L, True), self.Y, check_finite=False)
+        self.t_dense += time.perf_counter() - t1
 
     def _dK_theta(self, p):
         """dK/d log theta_p as the dense symmetric matrix the reference stores
@@ -216,12 +225,19 @@ class GP:
         ndk = P + (N * D if self.with_obs else 0)
         if mode == "literal":
             for p in range(ndk):
+                t0 = time.perf_counter()
                 dK = self._dK_theta(p) if p < P else self._dK_input((p - P) // D, (p - P) % D)
+                t1 = time.perf_counter()
                 r0 = a @ dK
                 r1 = sla.cho_solve((self.L, True), dK, check_finite=False)
                 grad[p] = 0.5 * np.trace(r0 - r1)
+                self.t_elem += t1 - t0
+                self.t_dense += time.perf_counter() - t1
         else:
+            t0 = time.perf_counter()
             Kinv = sla.cho_solve((self.L, True), np.eye(N), check_finite=False)
+            self.t_dense += time.perf_counter() - t0
+            t0 = time.perf_counter()
             W = a - Kinv
             for p in range(P):
                 grad[p] = 0.5 * np.sum(W * self._dK_theta(p))
@@ -242,6 +258,7 @@ class GP:
                     if gn is not None:
                         g += 0.5 * dg * gn
                     grad[P + d:P + N * D:D] = g
+            self.t_elem += time.perf_counter() - t0
         if self.with_obs:
             grad[ndk:] = -self.Alpha
         self.dK = None
