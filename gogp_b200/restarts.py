@@ -1,0 +1,59 @@
+"""Multi-start restart sharding (BASELINE configs[3]).
+
+Independent hyper-parameter restarts are separate optimisations over the same
+(X, Y): they shard across GPUs with NO data-path collective -- one process per
+GPU, one device handle per process; the only exchange is a host-side gather of
+(LML, theta) per restart at the end.  `evaluate` is any callable
+theta -> (lml, grad); on the product path it is gp.GP.Observe + Gradient.
+"""
+import numpy as np
+
+
+def shard(n_restarts, rank, world):
+    """Restart indices owned by `rank`: round-robin, so every rank gets
+    floor or ceil of n/world units."""
+    return list(range(rank, n_restarts, world))
+
+
+def adam_ascent(evaluate, theta0, iters, rate=0.01, beta1=0.9, beta2=0.999, eps=1e-8, threshold=1e-6):
+    """The tutorial's Adam loop (tutorial/tutorial.go:156-168: RATE 0.01, stop when
+    every |g| < THRESHOLD), maximising the log marginal likelihood."""
+    theta = np.array(theta0, dtype=np.float64)
+    m = np.zeros_like(theta)
+    v = np.zeros_like(theta)
+    lml = None
+    for t in range(1, iters + 1):
+        lml, g = evaluate(theta.copy())
+        if np.all(np.abs(g) < threshold):
+            break
+        m = beta1 * m + (1 - beta1) * g
+        v = beta2 * v + (1 - beta2) * g * g
+        theta = theta + rate * (m / (1 - beta1 ** t)) / (np.sqrt(v / (1 - beta2 ** t)) + eps)
+    lml, _ = evaluate(theta.copy())
+    return lml, theta
+
+
+def multi_start(evaluate, starts, rank=0, world=1, iters=0, dist=None):
+    """Run this rank's share of `starts` (R x P array, identical on every rank) and
+    gather all results.  Returns (lmls[R], thetas[R, P], best index); every rank
+    gets the same answer.  `dist` is torch.distributed (any backend) or None."""
+    starts = np.asarray(starts, dtype=np.float64)
+    R, P = starts.shape
+    lmls = np.full(R, -np.inf)
+    thetas = np.array(starts, copy=True)
+    for r in shard(R, rank, world):
+        if iters > 0:
+            lmls[r], thetas[r] = adam_ascent(evaluate, starts[r], iters)
+        else:
+            lmls[r], _ = evaluate(starts[r].copy())
+    if world > 1:
+        import torch
+        mine = torch.from_numpy(np.concatenate([lmls[:, None], thetas], axis=1))
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)  # R*(P+1) doubles per rank: the only exchange
+        for w, part in enumerate(parts):
+            idx = shard(R, w, world)
+            a = part.numpy()
+            lmls[idx] = a[idx, 0]
+            thetas[idx] = a[idx, 1:]
+    return lmls, thetas, int(np.argmax(lmls))
