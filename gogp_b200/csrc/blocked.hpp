@@ -19,7 +19,7 @@ namespace gogp {
 
 constexpr int64_t kTile = 128;
 
-enum : int { BL_FULL = 0, BL_LOWER = 1, BL_KTRI = 2, BL_DIAG_OUT = 4 };  // == GemmMode
+enum : int { BL_FULL = 0, BL_LOWER = 1, BL_KTRI = 2, BL_DIAG_OUT = 4, BL_INPLACE = 8 };  // == GemmMode
 
 template <class BE>
 struct Blocked {
@@ -49,7 +49,7 @@ struct Blocked {
     void trsm(double* B, int64_t ldb, int64_t m, int64_t o, int64_t n) {
         if (n == kTile) {
             // X = B Winv^T, in place: one CTA owns a full 128-row block of B (n == BN)
-            be.gemm(B, ldb, B, ldb, winv + (o / kTile) * kTile * kTile, kTile, m, kTile, kTile, 1.0, 0.0, BL_FULL,
+            be.gemm(B, ldb, B, ldb, winv + (o / kTile) * kTile * kTile, kTile, m, kTile, kTile, 1.0, 0.0, BL_INPLACE,
                     nullptr);
             return;
         }

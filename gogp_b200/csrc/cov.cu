@@ -44,14 +44,9 @@ __device__ __forceinline__ void stage_tiles(double* xr, double* xc, uint64_t* ba
 __device__ __forceinline__ double eval_program(const DevProgram& prog, const double* xc, int c, const double* xr,
                                                int r) {
     double k = 0.0;
-    for (int t = 0; t < prog.nterms; ++t) {
-        double p = prog.coef[t];
-        for (int fi = prog.fbeg[t]; fi < prog.fbeg[t + 1]; ++fi) {
-            const DevFactor& f = prog.f[fi];
-            p *= factor_value(f, xc[f.dim * TILE + c], xr[f.dim * TILE + r]);
-        }
-        k += p;
-    }
+    auto xa = [&](int d) { return xc[d * TILE + c]; };
+    auto xb = [&](int d) { return xr[d * TILE + r]; };
+    for (int t = 0; t < prog.nterms; ++t) k += term_value(prog, t, xa, xb);
     return k;
 }
 
@@ -124,15 +119,8 @@ __global__ void cov_self_kernel(const __grid_constant__ DevProgram prog, const d
     int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (m >= M) return;
     double k = 0.0;
-    for (int t = 0; t < prog.nterms; ++t) {
-        double p = prog.coef[t];
-        for (int fi = prog.fbeg[t]; fi < prog.fbeg[t + 1]; ++fi) {
-            const DevFactor& f = prog.f[fi];
-            double z = Zt[f.dim * Mpad + m];
-            p *= factor_value(f, z, z);
-        }
-        k += p;
-    }
+    auto z = [&](int d) { return Zt[d * Mpad + m]; };
+    for (int t = 0; t < prog.nterms; ++t) k += term_value(prog, t, z, z);
     kss[m] = k;
 }
 
@@ -218,12 +206,9 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
             for (int e = 0; e < GT_E; ++e) {
                 const int r = chunk * 64 + (e >> 1) * 4 + ir;
                 const int c = c0 + (e & 1);
-                double p = prog.coef[t];
-                for (int fi = fb; fi < fe; ++fi) {
-                    const DevFactor& f = prog.f[fi];
-                    p *= factor_value(f, xc[f.dim * TILE + c], xr[f.dim * TILE + r]);
-                }
-                pw[e * 256 + tid] = ww[e * 256 + tid] * p;
+                auto xa = [&](int d) { return xc[d * TILE + c]; };
+                auto xb = [&](int d) { return xr[d * TILE + r]; };
+                pw[e * 256 + tid] = ww[e * 256 + tid] * term_value(prog, t, xa, xb);
             }
             // phase 2: per-factor log-derivatives
             for (int fi = fb; fi < fe; ++fi) {
@@ -311,16 +296,15 @@ __global__ void __launch_bounds__(256) grad_inputs_kernel(const __grid_constant_
             double kv = (th == tl) ? kdiag[th * TILE * TILE + (hi % TILE) * TILE + (lo % TILE)] : kinv[hi * ld + lo];
             const double W = ai * alpha[j] - kv;
             double dk = 0.0;
+            auto xa = [&](int dd) { return Xt[dd * ldx + i]; };
+            auto xb = [&](int dd) { return Xt[dd * ldx + j]; };
             for (int t = 0; t < prog.nterms; ++t) {
-                double p = prog.coef[t];
                 double g = 0.0;
                 for (int fi = prog.fbeg[t]; fi < prog.fbeg[t + 1]; ++fi) {
                     const DevFactor& f = prog.f[fi];
-                    const double xa = Xt[f.dim * ldx + i], xb = Xt[f.dim * ldx + j];
-                    p *= factor_value(f, xa, xb);
-                    if (f.dim == d && f.kind != F_PARAM) g += factor_dlog_xa(f, xa, xb);
+                    if (f.dim == d && f.kind != F_PARAM) g += factor_dlog_xa(f, xa(d), xb(d));
                 }
-                dk += p * g;
+                if (g != 0.0) dk += term_value(prog, t, xa, xb) * g;
             }
             s += W * dk;
         }

@@ -14,6 +14,7 @@
 // [row][k] with a row pitch of 20 doubles: a half-warp's fragment read touches
 // rows r..r+3 x k..k+3 -> word offsets (20r + k)*2, all 32 banks distinct.
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "kexpr.cuh"
@@ -22,10 +23,8 @@ namespace gogp {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
-constexpr int PITCH = BK + 4;                      // doubles
-constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;   // A tile then B tile
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+constexpr int BK = 16;
+constexpr int PITCH = BK + 4;  // doubles
 
 struct GemmArgs {
     double* C;
@@ -54,17 +53,29 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(const GemmArgs g) {
+// Warp tile is always 64 x 32 (8 x 4 DMMA fragments); the CTA tile is
+// (64*WM) x (32*WN).  Two shipped shapes:
+//   <2,4,4,1>  128 x 128, 256 threads, 4 stages (160 KB), 1 CTA/SM -- required when C aliases A
+//              (in-place solve with a diagonal block: one CTA must own whole rows);
+//   <2,2,3,2>  128 x 64, 128 threads, 3 stages (90 KB), 2 CTAs/SM: the two resident CTAs
+//              synchronise independently, so one computes while the other sits at its barrier.
+template <int WM, int WN, int STAGES, int MINB>
+__global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_nt_kernel(const GemmArgs g) {
+    constexpr int BM = 64 * WM, BN = 32 * WN, NT = WM * WN * 32;
+    constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;
+    constexpr int RATIO = BM / BN > 0 ? BM / BN : 1;  // column tiles per diagonal block (BM >= BN)
     extern __shared__ __align__(128) double smem[];
     int ti, tj;
     if (g.mode & GEMM_LOWER) {
-        lower_tile(blockIdx.x, ti, tj);
+        int tg;
+        lower_tile(blockIdx.x / RATIO, ti, tg);
+        tj = tg * RATIO + blockIdx.x % RATIO;
     } else {
         ti = blockIdx.x / g.tn;
         tj = blockIdx.x % g.tn;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+    const int wm = warp / WN, wn = warp % WN;
     const int64_t row0 = (int64_t)ti * BM, col0 = (int64_t)tj * BN;
     const int k_lo = (g.mode & GEMM_KTRI) ? ti * BM : 0;
     const int nk = (g.k - k_lo) / BK;
@@ -72,16 +83,20 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(const GemmArgs g) {
     const double* Ag = g.A + row0 * g.lda + k_lo;
     const double* Bg = g.B + col0 * g.ldb + k_lo;
 
-    // each thread copies 4 16-byte chunks of A and 4 of B per stage
     auto load_stage = [&](int stage, int kt) {
         double* sa = smem + stage * STAGE_DOUBLES;
         double* sb = sa + BM * PITCH;
         const int64_t koff = (int64_t)kt * BK;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = tid + q * 256;
+        for (int q = 0; q < BM * 8 / NT; ++q) {
+            const int c = tid + q * NT;
             const int r = c >> 3, kc = (c & 7) * 2;
             cp_async16(sa + r * PITCH + kc, Ag + (int64_t)r * g.lda + koff + kc);
+        }
+#pragma unroll
+        for (int q = 0; q < BN * 8 / NT; ++q) {
+            const int c = tid + q * NT;
+            const int r = c >> 3, kc = (c & 7) * 2;
             cp_async16(sb + r * PITCH + kc, Bg + (int64_t)r * g.ldb + koff + kc);
         }
     };
@@ -127,9 +142,9 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(const GemmArgs g) {
     // epilogue: thread holds C[row][col..col+1] per fragment
     double* Cb;
     int64_t ldc;
-    if ((g.mode & GEMM_DIAG_OUT) && ti == tj) {
-        Cb = g.cdiag + (int64_t)ti * BM * BN;
-        ldc = BN;
+    if ((g.mode & GEMM_DIAG_OUT) && tj / RATIO == ti) {
+        Cb = g.cdiag + (int64_t)ti * BM * BM + (tj % RATIO) * BN;
+        ldc = BM;
     } else {
         Cb = g.C + row0 * g.ldc + col0;
         ldc = g.ldc;
@@ -150,6 +165,27 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(const GemmArgs g) {
             }
             *p = v;
         }
+}
+
+template <int WM, int WN, int STAGES, int MINB>
+void launch_cfg(const GemmArgs& g0, int64_t m, int64_t n, cudaStream_t s) {
+    constexpr int BM = 64 * WM, BN = 32 * WN;
+    constexpr size_t SMEM = (size_t)STAGES * (BM + BN) * PITCH * sizeof(double);
+    static bool configured[64] = {false};  // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(dgemm_nt_kernel<WM, WN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM);
+        configured[dev & 63] = true;
+    }
+    GemmArgs g = g0;
+    g.tm = (int)(m / BM);
+    g.tn = (int)(n / BN);
+    const int ratio = BM / BN;
+    const int ntiles = (g.mode & GEMM_LOWER) ? ratio * g.tm * (g.tm + 1) / 2 : g.tm * g.tn;
+    if (ntiles <= 0) return;
+    dgemm_nt_kernel<WM, WN, STAGES, MINB><<<ntiles, WM * WN * 32, SMEM, s>>>(g);
 }
 
 // ---- FP64 peak microbenchmarks (registers only) --------------------------------------
@@ -187,15 +223,16 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* sink)
 
 }  // namespace
 
+static int g_gemm_cfg = -1;  // 0: 128x128 1 CTA/SM, 1: 128x64 2 CTAs/SM (env GOGP_GEMM_CFG, default 1)
+void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
+
 void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s) {
-    static bool configured[64] = {false};  // the attribute is per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-        configured[dev & 63] = true;
+    if (g_gemm_cfg < 0) {
+        const char* e = getenv("GOGP_GEMM_CFG");
+        g_gemm_cfg = e ? atoi(e) : 1;
     }
+    if (k <= 0) return;
     GemmArgs g;
     g.C = C;
     g.A = A;
@@ -204,15 +241,16 @@ void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const
     g.ldc = ldc;
     g.lda = lda;
     g.ldb = ldb;
-    g.tm = (int)(m / BM);
-    g.tn = (int)(n / BN);
+    g.tm = g.tn = 0;
     g.k = (int)k;
     g.mode = mode;
     g.alpha = alpha;
     g.beta = beta;
-    int ntiles = (mode & GEMM_LOWER) ? g.tm * (g.tm + 1) / 2 : g.tm * g.tn;
-    if (ntiles <= 0 || k <= 0) return;
-    dgemm_nt_kernel<<<ntiles, 256, GEMM_SMEM, s>>>(g);
+    // C aliasing A needs a CTA that owns entire rows of the (128-wide) block
+    if (g_gemm_cfg == 0 || (mode & GEMM_INPLACE))
+        launch_cfg<2, 4, 4, 1>(g, m, n, s);
+    else
+        launch_cfg<2, 2, 3, 2>(g, m, n, s);
 }
 
 // variant = nacc_index * 4 + ctas_index; nacc in {8, 16, 32}, CTAs per SM in {1, 2, 4, 8}

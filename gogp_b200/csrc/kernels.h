@@ -41,10 +41,12 @@ enum GemmMode : int {
     GEMM_LOWER = 1,     // only tiles ti >= tj (SYRK / LAUUM)
     GEMM_KTRI = 2,      // A is upper triangular w.r.t. its own origin: k starts at ti*128
     GEMM_DIAG_OUT = 4,  // diagonal tiles go to cdiag ([T][128][128]) instead of C
+    GEMM_INPLACE = 8,   // C aliases A (n == 128): one CTA must own entire rows of the block
 };
 // C[i][j] = beta*C[i][j] + alpha * sum_k A[i][k] B[j][k]; all of m, n, k multiples of 128.
 void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s);
+void set_gemm_config(int cfg);  // 0: 128x128 tiles, 1 CTA/SM; 1: 128x64 tiles, 2 CTAs/SM
 // register-only issue-rate microbenchmarks: which = 0 DMMA m8n8k4, 1 DFMA
 int fp64_peak_variants();
 void launch_fp64_peak(int which, int variant, int iters, double* sink, cudaStream_t s);

@@ -14,12 +14,14 @@ namespace gogp {
 #define GOGP_SQRT5 2.2360679774997900
 #define GOGP_PI 3.14159265358979323846
 
+// Length-scale divisions use the host-computed reciprocal i0 = 1/(scale*theta)
+// (d differs from the reference's r/l by at most one ulp).
 __device__ __forceinline__ double factor_value(const DevFactor& f, double xa, double xb) {
     switch (f.kind) {
         case F_PARAM:
             return f.a0;
         case F_NORMAL: {
-            double d = (xa - xb) / f.a0;
+            double d = (xa - xb) * f.i0;
             return exp(-d * d / 2);
         }
         case F_PERIODIC: {
@@ -27,14 +29,38 @@ __device__ __forceinline__ double factor_value(const DevFactor& f, double xa, do
             return exp(-2 * d * d);
         }
         case F_MATERN32: {
-            double d = fabs(xa - xb) / f.a0;
+            double d = fabs(xa - xb) * f.i0;
             return (1 + GOGP_SQRT3 * d) * exp(-GOGP_SQRT3 * d);
         }
         default: {  // F_MATERN52
-            double d = fabs(xa - xb) / f.a0;
+            double d = fabs(xa - xb) * f.i0;
             return (1 + GOGP_SQRT5 * d + f.c * d * d) * exp(-GOGP_SQRT5 * d);
         }
     }
+}
+
+// Value of product term t at (xa, xb); XA / XB map an input dimension to the
+// coordinate.  The leading Normal factors of a term (the host sorts them first)
+// share one exponential: prod_d exp(-d_d^2/2) = exp(-(sum_d d_d^2)/2).
+template <class XA, class XB>
+__device__ __forceinline__ double term_value(const DevProgram& prog, int t, XA xa, XB xb) {
+    double p = prog.coef[t];
+    int fi = prog.fbeg[t];
+    const int fn = fi + prog.nnorm[t], fe = prog.fbeg[t + 1];
+    if (fi < fn) {
+        double q = 0.0;
+        for (; fi < fn; ++fi) {
+            const DevFactor& f = prog.f[fi];
+            const double d = (xa(f.dim) - xb(f.dim)) * f.i0;
+            q = fma(d, d, q);
+        }
+        p *= exp(-q / 2);
+    }
+    for (; fi < fe; ++fi) {
+        const DevFactor& f = prog.f[fi];
+        p *= factor_value(f, xa(f.dim), xb(f.dim));
+    }
+    return p;
 }
 
 // theta_q * (d f / d theta_q) / f for the (up to) two parameters of a factor.
@@ -45,7 +71,7 @@ __device__ __forceinline__ void factor_dlog_theta(const DevFactor& f, double xa,
             g0 = 1.0;
             return;
         case F_NORMAL: {
-            double d = (xa - xb) / f.a0;
+            double d = (xa - xb) * f.i0;
             g0 = d * d;
             return;
         }
@@ -59,12 +85,12 @@ __device__ __forceinline__ void factor_dlog_theta(const DevFactor& f, double xa,
             return;
         }
         case F_MATERN32: {
-            double d = fabs(xa - xb) / f.a0;
+            double d = fabs(xa - xb) * f.i0;
             g0 = 3 * d * d / (1 + GOGP_SQRT3 * d);
             return;
         }
         default: {
-            double d = fabs(xa - xb) / f.a0;
+            double d = fabs(xa - xb) * f.i0;
             g0 = d * d * (5 - 2 * f.c + GOGP_SQRT5 * f.c * d) / (1 + GOGP_SQRT5 * d + f.c * d * d);
             return;
         }
@@ -79,8 +105,8 @@ __device__ __forceinline__ double factor_dlog_xa(const DevFactor& f, double xa, 
         case F_PARAM:
             return 0.0;
         case F_NORMAL: {
-            double d = r / f.a0;
-            return -d / f.a0;
+            double d = r * f.i0;
+            return -d * f.i0;
         }
         case F_PERIODIC: {
             double u = GOGP_PI * fabs(r) / f.a1;
@@ -90,12 +116,12 @@ __device__ __forceinline__ double factor_dlog_xa(const DevFactor& f, double xa, 
             return -4 * d * c * GOGP_PI * sg / (f.a0 * f.a1);
         }
         case F_MATERN32: {
-            double d = fabs(r) / f.a0;
-            return -3 * d * sg / (f.a0 * (1 + GOGP_SQRT3 * d));
+            double d = fabs(r) * f.i0;
+            return -3 * d * sg * f.i0 / (1 + GOGP_SQRT3 * d);
         }
         default: {
-            double d = fabs(r) / f.a0;
-            return -d * (5 - 2 * f.c + GOGP_SQRT5 * f.c * d) * sg / (f.a0 * (1 + GOGP_SQRT5 * d + f.c * d * d));
+            double d = fabs(r) * f.i0;
+            return -d * (5 - 2 * f.c + GOGP_SQRT5 * f.c * d) * sg * f.i0 / (1 + GOGP_SQRT5 * d + f.c * d * d);
         }
     }
 }

@@ -10,57 +10,77 @@ namespace gogp {
 
 namespace {
 
-constexpr int LP = 129;  // smem pitch (doubles): odd -> column walks are conflict-free
+constexpr int LP = 132;  // smem pitch (doubles), = 4 mod 16: a half-warp = 4 rows x 4 k-phases hits 16 distinct 8-byte banks
 
-// Right-looking Cholesky of one 128x128 tile held in shared memory, fused with a
-// Gauss-Jordan build of the inverse: after column j of L is final, row j of
-// W = L^-1 is final too, and the rank-1 step that updates the trailing block
-// of A also updates rows i > j of W.  W[i][c] (c <= i) lives at S[c][i+1], the
-// unused upper triangle of the same array.
+// Cholesky (Crout, column by column) of one 128x128 tile held in shared memory,
+// fused with the inverse W = L^-1 built row by row one step behind: at step j
+// the threads of rows r >= j form column j of L (dot products of rows r and j
+// over k < j), while the threads of rows r < j -- idle in a plain Crout sweep --
+// form row j-1 of W,  W[j-1][r] = -(sum_{k=r}^{j-2} L[j-1][k] W[k][r]) / L[j-1][j-1].
+// Four threads share a row and split k by k mod 4; one barrier per column.
+// W[i][c] (c <= i) lives at S[c][i+1], the unused upper triangle of the array.
 __global__ void __launch_bounds__(512, 1) potrf_leaf_kernel(double* __restrict__ A, int64_t ld,
                                                             double* __restrict__ winv, int* __restrict__ info,
                                                             int base) {
     extern __shared__ double S[];  // [128][LP]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < TILE * TILE; idx += 512) {
-        const int r = idx >> 7, c = idx & 127;
-        S[r * LP + c] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
+    __shared__ double adiag[TILE];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < TILE * LP; idx += 512) {
+        const int r = idx / LP, c = idx - r * LP;
+        S[idx] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
     }
-    if (tid < TILE) S[tid * LP + TILE] = 0.0;
-    __syncthreads();
-    if (tid < TILE) S[tid * LP + tid + 1] = 1.0;  // W = I
+    if (tid < TILE) adiag[tid] = A[(int64_t)tid * ld + tid];
     __syncthreads();
 
-    for (int j = 0; j < TILE; ++j) {
-        double ajj = S[j * LP + j];
-        if (!(ajj > 0.0)) {  // not positive definite (or NaN): flag and keep going
-            if (tid == 0 && atomicCAS(info, 0, base + j + 1) == 0) {
+    const int r = tid >> 2, h = tid & 3;
+    const double* Sr = S + r * LP;
+    for (int j = 0; j <= TILE; ++j) {
+        double s = 0.0, p = 0.0;
+        if (r >= j) {
+            if (j < TILE) {
+                const double* Sj = S + j * LP;
+#pragma unroll 4
+                for (int k = h; k < j; k += 4) {
+                    const double lj = Sj[k];
+                    s = fma(Sr[k], lj, s);
+                    p = fma(lj, lj, p);
+                }
             }
-            ajj = 1.0;
+        } else if (r < j - 1) {
+            const double* Sj = S + (j - 1) * LP;
+            const int k0 = r + ((h - r) & 3);  // smallest k >= r with k mod 4 == h
+#pragma unroll 4
+            for (int k = k0; k < j - 1; k += 4) s = fma(Sj[k], Sr[k + 1], s);
         }
-        const double d = sqrt(ajj);
-        __syncthreads();  // everyone has read the pivot
-        if (tid < TILE) {
-            if (tid > j)
-                S[tid * LP + j] /= d;
-            else if (tid == j)
-                S[j * LP + j] = d;
-        } else if (tid < 2 * TILE) {
-            const int c = tid - TILE;
-            if (c <= j) S[c * LP + j + 1] /= d;
-        }
-        __syncthreads();
-        for (int i = j + 1 + warp; i < TILE; i += 16) {
-            const double lij = S[i * LP + j];
-            for (int k = j + 1 + lane; k <= i; k += 32) S[i * LP + k] -= lij * S[k * LP + j];
-            for (int c = lane; c <= j; c += 32) S[c * LP + i + 1] -= lij * S[c * LP + j + 1];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        if (h == 0) {
+            if (r >= j) {
+                if (j < TILE) {
+                    double ajj = adiag[j] - p;
+                    if (!(ajj > 0.0)) {  // not positive definite (or NaN): flag, keep going
+                        if (r == j) atomicCAS(info, 0, base + j + 1);
+                        ajj = 1.0;
+                    }
+                    const double d = sqrt(ajj);
+                    if (r == j)
+                        S[j * LP + j] = d;
+                    else
+                        S[r * LP + j] = (Sr[j] - s) / d;
+                }
+            } else {
+                const double dj = S[(j - 1) * LP + (j - 1)];
+                S[r * LP + j] = (r == j - 1) ? 1.0 / dj : -s / dj;
+            }
         }
         __syncthreads();
     }
     for (int idx = tid; idx < TILE * TILE; idx += 512) {
-        const int r = idx >> 7, c = idx & 127;
-        A[(int64_t)r * ld + c] = (c <= r) ? S[r * LP + c] : 0.0;
-        winv[idx] = (c <= r) ? S[c * LP + r + 1] : 0.0;
+        const int rr = idx >> 7, c = idx & 127;
+        A[(int64_t)rr * ld + c] = (c <= rr) ? S[rr * LP + c] : 0.0;
+        winv[idx] = (c <= rr) ? S[c * LP + rr + 1] : 0.0;
     }
 }
 
@@ -78,70 +98,112 @@ __global__ void __launch_bounds__(256) trtri_leaf_kernel(const double* __restric
     }
 }
 
-// One step of the blocked forward solve  L z = y  (w is the running right-hand
-// side): every CTA recomputes z_I = Winv_I w_I; CTA 0 stores it, CTA b >= 1
-// updates w_{I+b} -= L[I+b, I] z_I.
-__global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ld,
-                                                            const double* __restrict__ winv, double* __restrict__ w,
-                                                            double* __restrict__ z, int I) {
-    __shared__ double ws[TILE], zs[TILE];
+// 128-row block times a 128-vector held in registers (4 contiguous columns per
+// lane): every lane issues all of its loads before the first reduction.
+template <int ROWS>
+__device__ __forceinline__ void block_matvec(const double* __restrict__ M, int64_t ldm, const double* vs, int lane,
+                                             double (&out)[ROWS]) {
+    const double v0 = vs[4 * lane], v1 = vs[4 * lane + 1], v2 = vs[4 * lane + 2], v3 = vs[4 * lane + 3];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+        const double2* p = reinterpret_cast<const double2*>(M + (int64_t)rr * ldm + 4 * lane);
+        const double2 a = p[0], b = p[1];
+        out[rr] = a.x * v0 + a.y * v1 + b.x * v2 + b.y * v3;
+    }
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) out[rr] += __shfl_xor_sync(0xffffffffu, out[rr], o);
+}
+
+// out[lane] without dynamic register indexing
+template <int ROWS>
+__device__ __forceinline__ double pick(const double (&out)[ROWS], int lane) {
+    double v = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr)
+        if (lane == rr) v = out[rr];
+    return v;
+}
+
+// z_0 = Winv_0 w_0 (forward) -- the first block of the pipelined solves below.
+__global__ void __launch_bounds__(256) trsv_first_kernel(const double* __restrict__ winv,
+                                                         const double* __restrict__ w, double* __restrict__ z,
+                                                         int I, int transposed) {
+    __shared__ double ws[TILE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < TILE) ws[tid] = w[(int64_t)I * TILE + tid];
     __syncthreads();
     const double* Wi = winv + (int64_t)I * TILE * TILE;
-    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+    if (!transposed) {
+        double out[16];
+        block_matvec<16>(Wi + (int64_t)warp * 16 * TILE, TILE, ws, lane, out);
+        if (lane < 16) z[(int64_t)I * TILE + warp * 16 + lane] = pick(out, lane);  // every lane holds all 16 sums
+    } else if (tid < TILE) {
         double s = 0.0;
-        for (int c = lane; c <= r; c += 32) s += Wi[r * TILE + c] * ws[c];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) zs[r] = s;
-    }
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        if (tid < TILE) z[(int64_t)I * TILE + tid] = zs[tid];
-        return;
-    }
-    const int64_t rb = ((int64_t)I + blockIdx.x) * TILE;
-    const double* Lb = L + rb * ld + (int64_t)I * TILE;
-    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-        double s = 0.0;
-        for (int c = lane; c < TILE; c += 32) s += Lb[(int64_t)r * ld + c] * zs[c];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) w[rb + r] -= s;
+        for (int r = tid; r < TILE; ++r) s += Wi[r * TILE + tid] * ws[r];
+        z[(int64_t)I * TILE + tid] = s;
     }
 }
 
-// One step of the blocked backward solve  L^T x = z: x_I = Winv_I^T w_I; CTA b >= 1
-// updates w_J -= L[I, J]^T x_I for J = b - 1 < I.
+// One step of the blocked forward solve  L z = y  (w is the running right-hand
+// side, z_I is already known): CTA b updates w_{I+1+b} -= L[I+1+b, I] z_I; CTA 0,
+// whose block is then final, also produces z_{I+1} = Winv_{I+1} w_{I+1}, so a
+// step is one launch and no CTA recomputes anything.
+__global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ld,
+                                                            const double* __restrict__ winv, double* __restrict__ w,
+                                                            double* __restrict__ z, int I) {
+    __shared__ double zs[TILE], ws[TILE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < TILE) zs[tid] = z[(int64_t)I * TILE + tid];
+    __syncthreads();
+    const int64_t rb = ((int64_t)I + 1 + blockIdx.x) * TILE;
+    double out[16];
+    block_matvec<16>(L + (rb + warp * 16) * ld + (int64_t)I * TILE, ld, zs, lane, out);
+    if (lane < 16) {
+        const double v = w[rb + warp * 16 + lane] - pick(out, lane);
+        w[rb + warp * 16 + lane] = v;
+        ws[warp * 16 + lane] = v;
+    }
+    if (blockIdx.x != 0) return;
+    __syncthreads();
+    const double* Wn = winv + ((int64_t)I + 1) * TILE * TILE;
+    block_matvec<16>(Wn + (int64_t)warp * 16 * TILE, TILE, ws, lane, out);
+    if (lane < 16) z[rb + warp * 16 + lane] = pick(out, lane);
+}
+
+// One step of the blocked backward solve  L^T x = z  (x_I already known): CTA b
+// updates w_J -= L[I, J]^T x_I for J = I-1-b; CTA 0 (J = I-1, final after this
+// update) also produces x_{I-1} = Winv_{I-1}^T w_{I-1}.
 __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ld,
                                                             const double* __restrict__ winv, double* __restrict__ w,
                                                             double* __restrict__ x, int I) {
-    __shared__ double ws[TILE], xs[TILE], part[TILE];
+    __shared__ double xs[TILE], ws[TILE], part[TILE];
     const int tid = threadIdx.x;
-    if (tid < TILE) ws[tid] = w[(int64_t)I * TILE + tid];
+    if (tid < TILE) xs[tid] = x[(int64_t)I * TILE + tid];
     __syncthreads();
-    const double* Wi = winv + (int64_t)I * TILE * TILE;
-    {
-        // x[c] = sum_{r >= c} Winv[r][c] w[r]; two threads per column split the rows
-        const int c = tid & 127, half = tid >> 7;
-        double s = 0.0;
-        for (int r = c + half; r < TILE; r += 2) s += Wi[r * TILE + c] * ws[r];
-        if (half) part[c] = s;
-        __syncthreads();
-        if (!half) xs[c] = s + part[c];
-        __syncthreads();
-    }
-    if (blockIdx.x == 0) {
-        if (tid < TILE) x[(int64_t)I * TILE + tid] = xs[tid];
-        return;
-    }
-    const int64_t J = blockIdx.x - 1;
+    const int64_t J = (int64_t)I - 1 - blockIdx.x;
     const double* Lb = L + (int64_t)I * TILE * ld + J * TILE;
     const int c = tid & 127, half = tid >> 7;
     double s = 0.0;
+#pragma unroll 16
     for (int r = half * 64; r < half * 64 + 64; ++r) s += Lb[(int64_t)r * ld + c] * xs[r];
     if (half) part[c] = s;
     __syncthreads();
-    if (!half) w[J * TILE + c] -= s + part[c];
+    if (!half) {
+        const double v = w[J * TILE + c] - (s + part[c]);
+        w[J * TILE + c] = v;
+        ws[c] = v;
+    }
+    if (blockIdx.x != 0) return;
+    __syncthreads();
+    const double* Wn = winv + J * TILE * TILE;
+    s = 0.0;
+#pragma unroll 8
+    for (int r = c + half; r < TILE; r += 2) s += Wn[r * TILE + c] * ws[r];
+    if (half) part[c] = s;
+    __syncthreads();
+    if (!half) x[J * TILE + c] = s + part[c];
 }
 
 __global__ void __launch_bounds__(1024) logdet_dot_kernel(const double* __restrict__ L, int64_t ld,
@@ -242,9 +304,11 @@ void launch_trsv_lower(const double* L, int64_t ld, const double* winv, double* 
     // CTA 0 of a step stores block I of the result while the others still read rhs_I.
     const int T = (int)(Npad / TILE);
     if (!transposed) {
-        for (int I = 0; I < T; ++I) trsv_fwd_step_kernel<<<T - I, 256, 0, s>>>(L, ld, winv, rhs, out, I);
+        trsv_first_kernel<<<1, 256, 0, s>>>(winv, rhs, out, 0, 0);
+        for (int I = 0; I + 1 < T; ++I) trsv_fwd_step_kernel<<<T - 1 - I, 256, 0, s>>>(L, ld, winv, rhs, out, I);
     } else {
-        for (int I = T - 1; I >= 0; --I) trsv_bwd_step_kernel<<<I + 1, 256, 0, s>>>(L, ld, winv, rhs, out, I);
+        trsv_first_kernel<<<1, 256, 0, s>>>(winv, rhs, out, T - 1, 1);
+        for (int I = T - 1; I > 0; --I) trsv_bwd_step_kernel<<<I, 256, 0, s>>>(L, ld, winv, rhs, out, I);
     }
     if (launches) *launches += T;
 }

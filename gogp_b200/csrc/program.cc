@@ -98,6 +98,13 @@ bool Program::lower(const gogp_op* ops, int n, int ntheta_, int ndim, bool allow
         return false;
     }
     terms = std::move(stack.back());
+    // Normal factors first within each term (stable): the device folds them into one exponential
+    for (HostTerm& t : terms) {
+        std::vector<HostFactor> a, b;
+        for (const HostFactor& f : t.f) (f.kind == F_NORMAL ? a : b).push_back(f);
+        a.insert(a.end(), b.begin(), b.end());
+        t.f = std::move(a);
+    }
     size_t nf = 0;
     for (const HostTerm& t : terms) nf += t.f.size();
     if (nf > (size_t)kMaxFactors) {
@@ -114,6 +121,8 @@ void Program::bind(const double* theta, DevProgram* out) const {
     for (int t = 0; t < out->nterms; ++t) {
         out->fbeg[t] = k;
         out->coef[t] = terms[t].coef;
+        out->nnorm[t] = 0;
+        for (const HostFactor& f : terms[t].f) out->nnorm[t] += f.kind == F_NORMAL;
         for (const HostFactor& f : terms[t].f) {
             DevFactor& d = out->f[k++];
             d.kind = f.kind;
@@ -122,6 +131,7 @@ void Program::bind(const double* theta, DevProgram* out) const {
             d.p1 = f.p1;
             d.a0 = f.s0 * theta[f.p0];
             d.a1 = f.p1 >= 0 ? f.s1 * theta[f.p1] : 0.0;
+            d.i0 = 1.0 / d.a0;
             d.c = f.c;
         }
     }

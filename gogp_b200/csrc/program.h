@@ -34,6 +34,7 @@ struct DevFactor {
     int dim;
     int p0, p1;      // theta indices (p1 < 0 when unused)
     double a0, a1;   // effective parameters scale*theta, refreshed per evaluation
+    double i0;       // 1 / a0
     double c;        // Matern52 d^2 coefficient
 };
 
@@ -41,6 +42,7 @@ struct DevProgram {
     int nterms;
     int ntheta;
     int fbeg[kMaxTerms + 1];
+    int nnorm[kMaxTerms];  // leading Normal factors of each term (they share one exp)
     double coef[kMaxTerms];
     DevFactor f[kMaxFactors];
 };
