@@ -31,10 +31,34 @@ struct Blocked {
     static int64_t split(int64_t n) { return (n / kTile / 2) * kTile; }
     double* at(double* M, int64_t r, int64_t c) const { return M + r * ld + c; }
 
+    int64_t rl_max = 0;    // diagonal blocks up to this size are factored right-looking (0: never)
+    int64_t cols_max = 0;  // diagonal blocks up to this size are inverted column-wise (0: never)
+
+    // Right-looking factorisation of a small diagonal block with 128-wide panels:
+    // 3 launches per panel and every GEMM has K = 128, so the chain of dependent
+    // kernels is 3n/128 short ones instead of the recursion's ~5n/128 longer ones.
+    // Used below rl_max, where launches are latency-bound and flops are negligible.
+    void potrf_rl(int64_t o, int64_t n) {
+        for (int64_t p = 0; p < n; p += kTile) {
+            double* wp = winv + ((o + p) / kTile) * kTile * kTile;
+            be.potrf_leaf(at(A, o + p, o + p), ld, wp, (int)(o + p));
+            const int64_t m = n - p - kTile;
+            if (m <= 0) break;
+            double* panel = at(A, o + p + kTile, o + p);
+            be.gemm(panel, ld, panel, ld, wp, kTile, m, kTile, kTile, 1.0, 0.0, BL_INPLACE, nullptr);
+            be.gemm(at(A, o + p + kTile, o + p + kTile), ld, panel, ld, panel, ld, m, m, kTile, -1.0, 1.0, BL_LOWER,
+                    nullptr);
+        }
+    }
+
     // A[o:o+n, o:o+n] = L L^T
     void potrf(int64_t o, int64_t n) {
         if (n == kTile) {
             be.potrf_leaf(at(A, o, o), ld, winv + (o / kTile) * kTile * kTile, (int)o);
+            return;
+        }
+        if (n <= rl_max) {
+            potrf_rl(o, n);
             return;
         }
         const int64_t n1 = split(n), n2 = n - n1;
@@ -60,9 +84,27 @@ struct Blocked {
     }
 
     // U[o:o+n, o:o+n] (upper, in Bm with the same ld) = L[o:o+n, o:o+n]^-T
+    // Small-block variant of trtri_t, one block column of U at a time:
+    //   U[J,J] = Winv_J^T,   U[I<J, J] = -(sum_{K=I}^{J-1} U[I,K] L[J,K]^T) Winv_J^T
+    // (3 launches per column instead of the recursion's nested solve chains).
+    void trtri_cols(double* Bm, int64_t o, int64_t n) {
+        for (int64_t c = 0; c < n; c += kTile) {
+            double* wc = winv + ((o + c) / kTile) * kTile * kTile;
+            be.trtri_leaf(wc, at(Bm, o + c, o + c), ld);
+            if (c == 0) continue;
+            double* col = at(Bm, o, o + c);
+            be.gemm(col, ld, at(Bm, o, o), ld, at(A, o + c, o), ld, c, kTile, c, -1.0, 0.0, BL_KTRI, nullptr);
+            be.gemm(col, ld, col, ld, wc, kTile, c, kTile, kTile, 1.0, 0.0, BL_INPLACE, nullptr);
+        }
+    }
+
     void trtri_t(double* Bm, int64_t o, int64_t n) {
         if (n == kTile) {
             be.trtri_leaf(winv + (o / kTile) * kTile * kTile, at(Bm, o, o), ld);
+            return;
+        }
+        if (n <= cols_max) {
+            trtri_cols(Bm, o, n);
             return;
         }
         const int64_t n1 = split(n), n2 = n - n1;

@@ -4,6 +4,7 @@
 // a kernel launch on the handle's stream.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -21,6 +22,26 @@ constexpr double kNoNoise = 1e-5;  // gp/gp.go:43
 constexpr int64_t kProduceChunk = 8192;
 
 inline int64_t pad_tile(int64_t n) { return n <= 0 ? 0 : ((n + TILE - 1) / TILE) * TILE; }
+
+// Diagonal blocks up to this size use the short-chain (right-looking / column-wise)
+// variants of blocked.hpp; above it the recursion keeps every GEMM's K large.
+inline int64_t rl_max() {
+    static int64_t v = -1;
+    if (v < 0) {
+        const char* e = getenv("GOGP_RL_MAX");
+        v = e ? atoll(e) : 4096;  // measured on B200 at N = 32768: potrf 431 ms (0) -> 412 ms (4096)
+    }
+    return v;
+}
+// The column-wise inverse measured slower than the recursion (potri 722 -> 728 ms at 2048): off by default.
+inline int64_t cols_max() {
+    static int64_t v = -1;
+    if (v < 0) {
+        const char* e = getenv("GOGP_COLS_MAX");
+        v = e ? atoll(e) : 0;
+    }
+    return v;
+}
 
 // Per-launch accounting of the GEMM (gogp_profile_enable).
 struct GemmProfile {
@@ -234,7 +255,7 @@ gogp_status absorb(gogp_handle* h) {
     CK(cudaEventRecord(h->ev[1], s));
 
     CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
-    Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
+    Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
     bl.potrf(0, Npad);
     CK(cudaEventRecord(h->ev[2], s));
 
@@ -414,7 +435,7 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
     CK(cudaEventRecord(h->ev[0], s));
     if (!h->have_kinv) {
         CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
-        Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
+        Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
         bl.trtri_t(h->dB, 0, Npad);
         bl.lauum(h->dB, h->dDg, Npad);
         h->have_kinv = true;
@@ -500,7 +521,7 @@ gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu,
             launch_cov_cross(prog, h->dXt, N, Npad, h->dZt, mc, mpad, D, h->dBt, s);
             launch_row_reduce(h->dBt, Npad, mc, Npad, h->dAlpha, dmu, s);  // mean = Kstar^T alpha, gp/gp.go:335
             CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
-            Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv};
+            Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
             bl.trsm(h->dBt, Npad, mpad, 0, Npad);                        // V^T = Kstar^T L^-T
             launch_row_reduce(h->dBt, Npad, mc, Npad, nullptr, dss, s);  // diag(Kstar^T K^-1 Kstar)
             h->launches += 3;

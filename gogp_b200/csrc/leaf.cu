@@ -35,23 +35,37 @@ __global__ void __launch_bounds__(512, 1) potrf_leaf_kernel(double* __restrict__
     const int r = tid >> 2, h = tid & 3;
     const double* Sr = S + r * LP;
     for (int j = 0; j <= TILE; ++j) {
-        double s = 0.0, p = 0.0;
+        // two independent accumulator chains per sum keep the FP64 pipe busy
+        double s0 = 0.0, s1 = 0.0, p0 = 0.0, p1 = 0.0;
         if (r >= j) {
             if (j < TILE) {
                 const double* Sj = S + j * LP;
-#pragma unroll 4
-                for (int k = h; k < j; k += 4) {
-                    const double lj = Sj[k];
-                    s = fma(Sr[k], lj, s);
-                    p = fma(lj, lj, p);
+                int k = h;
+#pragma unroll 2
+                for (; k + 4 < j; k += 8) {
+                    const double l0 = Sj[k], l1 = Sj[k + 4];
+                    s0 = fma(Sr[k], l0, s0);
+                    s1 = fma(Sr[k + 4], l1, s1);
+                    p0 = fma(l0, l0, p0);
+                    p1 = fma(l1, l1, p1);
+                }
+                if (k < j) {
+                    const double l0 = Sj[k];
+                    s0 = fma(Sr[k], l0, s0);
+                    p0 = fma(l0, l0, p0);
                 }
             }
         } else if (r < j - 1) {
             const double* Sj = S + (j - 1) * LP;
-            const int k0 = r + ((h - r) & 3);  // smallest k >= r with k mod 4 == h
-#pragma unroll 4
-            for (int k = k0; k < j - 1; k += 4) s = fma(Sj[k], Sr[k + 1], s);
+            int k = r + ((h - r) & 3);  // smallest k >= r with k mod 4 == h
+#pragma unroll 2
+            for (; k + 4 < j - 1; k += 8) {
+                s0 = fma(Sj[k], Sr[k + 1], s0);
+                s1 = fma(Sj[k + 4], Sr[k + 5], s1);
+            }
+            if (k < j - 1) s0 = fma(Sj[k], Sr[k + 1], s0);
         }
+        double s = s0 + s1, p = p0 + p1;
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         p += __shfl_xor_sync(0xffffffffu, p, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -64,15 +78,14 @@ __global__ void __launch_bounds__(512, 1) potrf_leaf_kernel(double* __restrict__
                         if (r == j) atomicCAS(info, 0, base + j + 1);
                         ajj = 1.0;
                     }
-                    const double d = sqrt(ajj);
                     if (r == j)
-                        S[j * LP + j] = d;
+                        S[j * LP + j] = sqrt(ajj);
                     else
-                        S[r * LP + j] = (Sr[j] - s) / d;
+                        S[r * LP + j] = (Sr[j] - s) * rsqrt(ajj);  // one reciprocal square root, no divide
                 }
             } else {
-                const double dj = S[(j - 1) * LP + (j - 1)];
-                S[r * LP + j] = (r == j - 1) ? 1.0 / dj : -s / dj;
+                const double dj = 1.0 / S[(j - 1) * LP + (j - 1)];
+                S[r * LP + j] = (r == j - 1) ? dj : -s * dj;
             }
         }
         __syncthreads();

@@ -90,12 +90,17 @@ struct HostBackend {
 
 }  // namespace
 
+static int64_t g_rl_max = 0;
+
 extern "C" {
+
+// diagonal blocks up to this size take the short-chain variants (0: pure recursion)
+void cpu_blocked_set_rl_max(int64_t v) { g_rl_max = v; }
 
 // A: n x n row-major (lower used), factored in place; winv: (n/128) x 128 x 128.
 int cpu_blocked_potrf(double* A, int64_t n, double* winv) {
     HostBackend be;
-    Blocked<HostBackend> bl{be, A, n, winv};
+    Blocked<HostBackend> bl{be, A, n, winv, g_rl_max, g_rl_max};
     bl.potrf(0, n);
     return be.info;
 }
@@ -103,7 +108,7 @@ int cpu_blocked_potrf(double* A, int64_t n, double* winv) {
 // L (from cpu_blocked_potrf) -> K^-1: strictly-lower tiles of Bm, diagonal tiles in dg.
 void cpu_blocked_kinv(double* L, int64_t n, double* winv, double* Bm, double* dg) {
     HostBackend be;
-    Blocked<HostBackend> bl{be, L, n, winv};
+    Blocked<HostBackend> bl{be, L, n, winv, g_rl_max, g_rl_max};
     bl.trtri_t(Bm, 0, n);
     bl.lauum(Bm, dg, n);
 }
@@ -111,14 +116,14 @@ void cpu_blocked_kinv(double* L, int64_t n, double* winv, double* Bm, double* dg
 // Only the transposed inverse U = L^-T (upper triangle of Bm).
 void cpu_blocked_trtri(double* L, int64_t n, double* winv, double* Bm) {
     HostBackend be;
-    Blocked<HostBackend> bl{be, L, n, winv};
+    Blocked<HostBackend> bl{be, L, n, winv, g_rl_max, g_rl_max};
     bl.trtri_t(Bm, 0, n);
 }
 
 // B (m x n) <- B L^-T
 void cpu_blocked_trsm(double* L, int64_t n, double* winv, double* B, int64_t m) {
     HostBackend be;
-    Blocked<HostBackend> bl{be, L, n, winv};
+    Blocked<HostBackend> bl{be, L, n, winv, g_rl_max, g_rl_max};
     bl.trsm(B, n, m, 0, n);
 }
 }

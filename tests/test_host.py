@@ -95,8 +95,10 @@ def _p(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+@pytest.mark.parametrize("rl_max", [0, 256, 1024])
 @pytest.mark.parametrize("n", [128, 384, 640])
-def test_blocked_recursion_on_host_backend(cpu_blocked, n):
+def test_blocked_recursion_on_host_backend(cpu_blocked, n, rl_max):
+    cpu_blocked.cpu_blocked_set_rl_max(C.c_int64(rl_max))
     rng = np.random.default_rng(n)
     G = rng.standard_normal((n, n))
     K = G @ G.T / n + np.eye(n)
@@ -120,6 +122,7 @@ def test_blocked_recursion_on_host_backend(cpu_blocked, n):
 
 
 def test_blocked_potrf_flags_non_pd(cpu_blocked):
+    cpu_blocked.cpu_blocked_set_rl_max(C.c_int64(0))
     n = 256
     K = np.eye(n)
     K[200, 200] = -1.0
