@@ -661,6 +661,133 @@ gogp_status gogp_debug_gemm(gogp_handle* h, int64_t n, int64_t k, int mode, int 
     return GOGP_OK;
 }
 
+// ---- device-level building blocks (multi-GPU block-cyclic factorisation) ---------------------
+static inline cudaStream_t pick_stream(gogp_handle* h, void* stream) {
+    return stream ? (cudaStream_t)stream : h->stream;
+}
+
+gogp_status gogp_dev_set_inputs(gogp_handle* h, const double* X, int64_t N) {
+    if (!h || !X || N <= 0) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    const int64_t Npad = pad_tile(N);
+    free_dev(h->dXraw);
+    free_dev(h->dXt);
+    h->cap = 0;  // the single-GPU buffers are not kept alongside
+    free_dev(h->dY); free_dev(h->dA); free_dev(h->dWinv); free_dev(h->dAlpha); free_dev(h->dW); free_dev(h->dZ);
+    free_dev(h->dGx); free_dev(h->dB); free_dev(h->dDg); free_dev(h->dPartial);
+    h->cap_grad = 0;
+    h->has_data = false;
+    h->factored = false;
+    CK(cudaMalloc(&h->dXraw, (size_t)Npad * h->ndim * sizeof(double)));
+    CK(cudaMalloc(&h->dXt, (size_t)Npad * h->ndim * sizeof(double)));
+    CK(cudaMemcpyAsync(h->dXraw, X, (size_t)N * h->ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_transpose_x(h->dXraw, h->dXt, N, Npad, h->ndim, h->stream);
+    ++h->launches;
+    CK(cudaStreamSynchronize(h->stream));
+    h->N = N;
+    h->Npad = Npad;
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_cov_block(gogp_handle* h, const double* theta_simil, const double* theta_noise, int64_t row0,
+                               int64_t rows, int64_t col0, int64_t cols, int diagonal, double* out, int64_t ld,
+                               void* stream) {
+    if (!h || !out || rows <= 0 || cols <= 0 || rows % TILE || cols % TILE || row0 % TILE || col0 % TILE)
+        return GOGP_BAD_ARGUMENT;
+    if (!h->dXt || row0 + rows > h->Npad || col0 + cols > h->Npad)
+        return fail(h, GOGP_BAD_ARGUMENT, "block outside the inputs set by gogp_dev_set_inputs");
+    if (diagonal && (row0 != col0 || rows != cols)) return fail(h, GOGP_BAD_ARGUMENT, "diagonal block must be square");
+    CK(cudaSetDevice(h->dev));
+    std::vector<double> ts(h->nts > 0 ? h->nts : 1, 0.0), tn(h->ntn > 0 ? h->ntn : 1, 0.0);
+    if (theta_simil)
+        for (int i = 0; i < h->nts; ++i) ts[i] = theta_simil[i];
+    if (theta_noise)
+        for (int i = 0; i < h->ntn; ++i) tn[i] = theta_noise[i];
+    set_theta(h, ts.data(), tn.data());
+    DevProgram prog;
+    h->simil.bind(h->theta_s.data(), &prog);
+    cudaStream_t s = pick_stream(h, stream);
+    if (diagonal)
+        launch_cov_sym_block(prog, h->dXt + row0, h->Npad, h->N - row0, (int)(rows / TILE), h->ndim, h->noise_var, out,
+                             ld, s);
+    else
+        launch_cov_rect_block(prog, h->dXt + row0, h->Npad, h->N - row0, (int)(rows / TILE), h->dXt + col0, h->Npad,
+                              h->N - col0, (int)(cols / TILE), h->ndim, out, ld, s);
+    ++h->launches;
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_potrf(gogp_handle* h, double* A, int64_t ld, int64_t n, double* winv, int* info, int base,
+                           void* stream) {
+    if (!h || !A || !winv || !info || n <= 0 || n % TILE) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    // the leaf reports base + local index: shift the matrix origin instead of the index
+    struct Shifted : CudaBackend {
+        int shift;
+        void potrf_leaf(double* At, int64_t l, double* w, int b) { CudaBackend::potrf_leaf(At, l, w, b + shift); }
+    } be{{pick_stream(h, stream), info, &h->launches, &h->prof}, base};
+    Blocked<Shifted> bl{be, A, ld, winv, rl_max(), cols_max()};
+    bl.potrf(0, n);
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_trsm(gogp_handle* h, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
+                          const double* winv, void* stream) {
+    if (!h || !B || !L || !winv || m <= 0 || n <= 0 || m % TILE || n % TILE) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    CudaBackend be{pick_stream(h, stream), h->dInfo, &h->launches, &h->prof};
+    Blocked<CudaBackend> bl{be, const_cast<double*>(L), ldl, const_cast<double*>(winv), rl_max(), cols_max()};
+    bl.trsm(B, ldb, m, 0, n);
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_gemm(gogp_handle* h, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
+                          int64_t ldb, int64_t m, int64_t n, int64_t k, double alpha, double beta, int lower,
+                          void* stream) {
+    if (!h || !C || !A || !B || m <= 0 || n <= 0 || k <= 0 || m % TILE || n % TILE || k % TILE) return GOGP_BAD_ARGUMENT;
+    if (lower && m != n) return fail(h, GOGP_BAD_ARGUMENT, "lower needs a square C");
+    CK(cudaSetDevice(h->dev));
+    CudaBackend be{pick_stream(h, stream), h->dInfo, &h->launches, &h->prof};
+    be.gemm(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, lower ? GEMM_LOWER : GEMM_FULL, nullptr);
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_sumlogdiag(gogp_handle* h, const double* L, int64_t ld, int64_t nvalid, double* out,
+                                void* stream) {
+    if (!h || !L || !out) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    // y = alpha = L's own storage is never dereferenced for i >= nvalid; pass L for both vectors' slots
+    launch_logdet_dot(L, ld, nullptr, nullptr, nvalid > 0 ? nvalid : 0, out, pick_stream(h, stream));
+    ++h->launches;
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_gemv_sub(gogp_handle* h, const double* B, int64_t ld, int64_t rows, int64_t cols,
+                              const double* v, double* acc, double* scratch, void* stream) {
+    if (!h || !B || !v || !acc || !scratch || rows <= 0 || cols <= 0) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    cudaStream_t s = pick_stream(h, stream);
+    launch_row_reduce(B, ld, rows, cols, v, scratch, s);
+    launch_axpy(acc, scratch, -1.0, rows, s);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_trsv(gogp_handle* h, const double* L, int64_t ld, const double* winv, double* rhs, double* z,
+                          int64_t n, void* stream) {
+    if (!h || !L || !winv || !rhs || !z || n <= 0 || n % TILE) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    launch_trsv_lower(L, ld, winv, rhs, z, n, false, pick_stream(h, stream), &h->launches);
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
 gogp_status gogp_timer_start(gogp_handle* h) {
     if (!h) return GOGP_BAD_ARGUMENT;
     CK(cudaSetDevice(h->dev));

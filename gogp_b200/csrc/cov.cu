@@ -106,6 +106,23 @@ void launch_cov_build(const DevProgram& prog, const double* Xt, int64_t N, int64
     cov_tile_kernel<true><<<ntiles, 256, smem, s>>>(prog, Xt, Npad, N, Xt, Npad, N, D, noise, out, Npad, T);
 }
 
+void launch_cov_sym_block(const DevProgram& prog, const double* Xt, int64_t ldx, int64_t nvalid, int tiles, int D,
+                          double noise, double* out, int64_t ld, cudaStream_t s) {
+    size_t smem = cov_smem(D);
+    cudaFuncSetAttribute(cov_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cov_tile_kernel<true><<<tiles * (tiles + 1) / 2, 256, smem, s>>>(prog, Xt, ldx, nvalid, Xt, ldx, nvalid, D, noise, out,
+                                                                   ld, tiles);
+}
+
+void launch_cov_rect_block(const DevProgram& prog, const double* Rt, int64_t ldr, int64_t rows_valid, int rtiles,
+                           const double* Ct, int64_t ldc, int64_t cols_valid, int ctiles, int D, double* out,
+                           int64_t ld, cudaStream_t s) {
+    size_t smem = cov_smem(D);
+    cudaFuncSetAttribute(cov_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cov_tile_kernel<false><<<rtiles * ctiles, 256, smem, s>>>(prog, Rt, ldr, rows_valid, Ct, ldc, cols_valid, D, 0.0, out,
+                                                             ld, ctiles);
+}
+
 void launch_cov_cross(const DevProgram& prog, const double* Xt, int64_t N, int64_t Npad, const double* Zt, int64_t M,
                       int64_t Mpad, int D, double* out, cudaStream_t s) {
     int tm = (int)(Mpad / TILE), tn = (int)(Npad / TILE);

@@ -19,6 +19,14 @@ void launch_cov_build(const DevProgram& prog, const double* Xt, int64_t N, int64
 // out[m][i] = k(xa = x_i, xb = z_m), Mpad x Npad (ld = Npad), zero padded.  gp/gp.go:322-332.
 void launch_cov_cross(const DevProgram& prog, const double* Xt, int64_t N, int64_t Npad, const double* Zt, int64_t M,
                       int64_t Mpad, int D, double* out, cudaStream_t s);
+// Block-wise builds for the multi-GPU block-cyclic layout: a diagonal block (lower tiles, noise on
+// the diagonal, identity beyond nvalid) and an off-diagonal block (full rectangle, zero padding).
+// Xt / Rt / Ct already point at the block's first row / column of the dimension-major inputs.
+void launch_cov_sym_block(const DevProgram& prog, const double* Xt, int64_t ldx, int64_t nvalid, int tiles, int D,
+                          double noise, double* out, int64_t ld, cudaStream_t s);
+void launch_cov_rect_block(const DevProgram& prog, const double* Rt, int64_t ldr, int64_t rows_valid, int rtiles,
+                           const double* Ct, int64_t ldc, int64_t cols_valid, int ctiles, int D, double* out,
+                           int64_t ld, cudaStream_t s);
 // kss[m] = k(z_m, z_m).  gp/gp.go:270-278.
 void launch_cov_self(const DevProgram& prog, const double* Zt, int64_t M, int64_t Mpad, int D, double* kss,
                      cudaStream_t s);
@@ -63,6 +71,8 @@ void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t
 // rhs (Npad) is destroyed; out must not alias it.
 void launch_trsv_lower(const double* L, int64_t ld, const double* winv, double* rhs, double* out, int64_t Npad,
                        bool transposed, cudaStream_t s, int64_t* launches);
+// y += a x
+void launch_axpy(double* y, const double* x, double a, int64_t n, cudaStream_t s);
 // v[i] = value for i in [0, n)
 void launch_fill(double* v, int64_t n, double value, cudaStream_t s);
 // pseudo-random fill in (-0.5, 0.5) for microbenchmarks

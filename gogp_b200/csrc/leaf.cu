@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(1024) logdet_dot_kernel(const double* __restri
     double s0 = 0.0, s1 = 0.0;
     for (int64_t i = threadIdx.x; i < N; i += 1024) {
         s0 += log(L[i * ld + i]);
-        s1 += y[i] * alpha[i];
+        if (y) s1 += y[i] * alpha[i];
     }
     a[threadIdx.x] = s0;
     b[threadIdx.x] = s1;
@@ -287,6 +287,14 @@ __global__ void fill_kernel(double* __restrict__ v, int64_t n, double value, int
 }
 
 }  // namespace
+
+__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ x, double a, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
+}
+void launch_axpy(double* y, const double* x, double a, int64_t n, cudaStream_t s) {
+    if (n > 0) axpy_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(y, x, a, n);
+}
 
 void launch_fill(double* v, int64_t n, double value, cudaStream_t s) {
     if (n > 0) fill_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(v, n, value, 0);

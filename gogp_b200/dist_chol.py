@@ -1,0 +1,256 @@
+"""2D block-cyclic Cholesky / log marginal likelihood across the GPUs of one box
+(BASELINE configs[4]: N = 131072 does not fit one GPU).
+
+One process per GPU.  K is cut into NB x NB blocks; block (I, J), J <= I, lives on
+process (I mod Pr, J mod Pc) of a Pr x Pc grid (rank = r * Pc + c), stored in a local
+row-major matrix whose block rows / columns are the owned ones in increasing order.
+Every rank builds its own blocks from the replicated inputs (no communication for
+the build).  Right-looking factorisation, one block column k at a time:
+
+  1. the owner of (k, k) factors it (single-GPU blocked Cholesky) and broadcasts
+     L_kk and its tile inverses;
+  2. the ranks of process column k mod Pc solve their part of the panel
+     A_Ik <- A_Ik L_kk^-T and broadcast it (NCCL over NVLink), so that every rank
+     holds the whole panel, organised by process row;
+  3. every rank updates its own trailing blocks A_IJ -= L_Ik L_Jk^T with the
+     DMMA GEMM, one launch per owned block row (M = NB, N = owned columns <= I, K = NB).
+
+This module is orchestration only: memory, views and collectives come from torch /
+torch.distributed (plumbing); every flop is a kernel of libgogp_b200.so reached
+through the device-level C-ABI (gogp_dev_*).  The compute backend is injected so
+that the same orchestration runs in a 2-rank gloo test on CPU with a NumPy backend
+that lives under tests/.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+class CudaBlocks:
+    """Compute backend: the gogp_dev_* entry points on torch CUDA tensors."""
+
+    def __init__(self, simil, noise, ndim, device):
+        import ctypes as C
+        from . import _lib
+        self.C, self._lib, self.L = C, _lib, _lib.lib()
+        self.device = torch.device("cuda", device)
+        sd = simil.Descriptor()
+        nd = noise.Descriptor() if noise is not None else None
+        self.h = C.c_void_p()
+        st = self.L.gogp_create(ndim, sd, len(sd), simil.NTheta(), nd, len(nd) if nd is not None else 0,
+                                noise.NTheta() if noise is not None else 0, device, C.byref(self.h))
+        self._ck(st)
+        self.info = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _ck(self, st):
+        if st != self._lib.OK:
+            raise RuntimeError("gogp: " + self.L.gogp_last_error(self.h).decode())
+
+    def _stream(self):
+        return self.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        assert t.stride(-1) == 1
+        return t.data_ptr()
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float64, device=self.device)
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64, device=self.device)
+
+    def set_inputs(self, X):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        self._ck(self.L.gogp_dev_set_inputs(self.h, self._lib.dptr(X.reshape(-1)), X.shape[0]))
+
+    def cov_block(self, theta_s, theta_n, row0, rows, col0, cols, diagonal, out):
+        ts = np.ascontiguousarray(theta_s, dtype=np.float64)
+        tn = np.ascontiguousarray(theta_n, dtype=np.float64)
+        self._ck(self.L.gogp_dev_cov_block(self.h, self._lib.dptr(ts), self._lib.dptr(tn), row0, rows, col0, cols,
+                                           1 if diagonal else 0, self._p(out), out.stride(0), self._stream()))
+
+    def potrf(self, A, winv, base):
+        self._ck(self.L.gogp_dev_potrf(self.h, self._p(A), A.stride(0), A.shape[0], self._p(winv),
+                                       self.info.data_ptr(), base, self._stream()))
+
+    def trsm(self, B, L, winv):
+        self._ck(self.L.gogp_dev_trsm(self.h, self._p(B), B.stride(0), B.shape[0], self._p(L), L.stride(0),
+                                      L.shape[0], self._p(winv), self._stream()))
+
+    def gemm(self, Cm, A, B, alpha, beta, lower=False):
+        self._ck(self.L.gogp_dev_gemm(self.h, self._p(Cm), Cm.stride(0), self._p(A), A.stride(0), self._p(B),
+                                      B.stride(0), Cm.shape[0], Cm.shape[1], A.shape[1], alpha, beta,
+                                      1 if lower else 0, self._stream()))
+
+    def sumlogdiag(self, Lb, nvalid, out2):
+        self._ck(self.L.gogp_dev_sumlogdiag(self.h, self._p(Lb), Lb.stride(0), nvalid, out2.data_ptr(),
+                                            self._stream()))
+
+    def gemv_sub(self, B, v, acc, scratch):
+        self._ck(self.L.gogp_dev_gemv_sub(self.h, self._p(B), B.stride(0), B.shape[0], B.shape[1], v.data_ptr(),
+                                          acc.data_ptr(), scratch.data_ptr(), self._stream()))
+
+    def trsv(self, Lb, winv, rhs, z):
+        self._ck(self.L.gogp_dev_trsv(self.h, self._p(Lb), Lb.stride(0), self._p(winv), rhs.data_ptr(),
+                                      z.data_ptr(), Lb.shape[0], self._stream()))
+
+    def bad_pivot(self):
+        return int(self.info.item())
+
+    def launches(self):
+        return int(self.L.gogp_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.gogp_destroy(self.h)
+            self.h = None
+
+
+def default_grid(world):
+    """Pr x Pc with Pr >= Pc: the panel solve is shared by the Pr ranks of one process
+    column, and with whole-panel broadcasts the shape does not change the traffic."""
+    pc = 1
+    while (pc * 2) * (pc * 2) <= world and world % (pc * 2) == 0:
+        pc *= 2
+    return world // pc, pc
+
+
+class BlockCyclicCholesky:
+    def __init__(self, backend, N, NB, rank=0, world=1, grid=None, dist=None):
+        assert NB % 128 == 0
+        self.be, self.N, self.NB, self.rank, self.world, self.dist = backend, N, NB, rank, world, dist
+        self.Pr, self.Pc = grid if grid is not None else default_grid(world)
+        assert self.Pr * self.Pc == world
+        self.r, self.c = rank // self.Pc, rank % self.Pc
+        self.nb = (N + NB - 1) // NB
+        self.my_rows = [I for I in range(self.nb) if I % self.Pr == self.r]
+        self.my_cols = [J for J in range(self.nb) if J % self.Pc == self.c]
+        self.ri = {I: i for i, I in enumerate(self.my_rows)}
+        self.ci = {J: j for j, J in enumerate(self.my_cols)}
+        self.local = backend.empty(max(1, len(self.my_rows)) * NB, max(1, len(self.my_cols)) * NB)
+        # the whole panel of the current step, organised by process row
+        self.rows_of = [[I for I in range(self.nb) if I % self.Pr == rr] for rr in range(self.Pr)]
+        self.panel = [backend.empty(max(1, len(self.rows_of[rr])), NB, NB) for rr in range(self.Pr)]
+        self.pc_buf = backend.empty(max(1, len(self.my_cols)), NB, NB)
+        self.lkk = backend.empty(NB, NB)
+        self.wkk = backend.empty(NB // 128, 128, 128)
+        self.winv_diag = {}   # tile inverses of the diagonal blocks this rank owns (for the solve)
+        self.logdet2 = backend.zeros(2)
+        self.sumlog = backend.zeros(1)
+        self.factored = False
+
+    def owner(self, I, J):
+        return (I % self.Pr) * self.Pc + (J % self.Pc)
+
+    def block(self, I, J):
+        i, j, NB = self.ri[I], self.ci[J], self.NB
+        return self.local[i * NB:(i + 1) * NB, j * NB:(j + 1) * NB]
+
+    def _bcast(self, t, src):
+        if self.world > 1:
+            self.dist.broadcast(t, src=src)
+
+    # ---- build: every rank evaluates its own blocks from the replicated inputs ----
+    def build(self, theta_simil, theta_noise):
+        NB = self.NB
+        for I in self.my_rows:
+            for J in self.my_cols:
+                if J <= I:
+                    self.be.cov_block(theta_simil, theta_noise, I * NB, NB, J * NB, NB, I == J, self.block(I, J))
+        self.factored = False
+
+    # ---- factor ---------------------------------------------------------------------
+    def factor(self):
+        NB, be = self.NB, self.be
+        self.sumlog.zero_()
+        for k in range(self.nb):
+            ok = self.owner(k, k)
+            if self.rank == ok:
+                d = self.block(k, k)
+                w = be.empty(NB // 128, 128, 128)
+                be.potrf(d, w, k * NB)
+                be.sumlogdiag(d, min(NB, self.N - k * NB), self.logdet2)
+                self.sumlog += self.logdet2[:1]
+                self.winv_diag[k] = w
+                self.lkk.copy_(d)
+                self.wkk.copy_(w)
+            if k == self.nb - 1:
+                break
+            self._bcast(self.lkk, ok)
+            self._bcast(self.wkk, ok)
+            # panel solve on the ranks of process column k mod Pc, then whole-panel broadcast
+            kc = k % self.Pc
+            for rr in range(self.Pr):
+                rows = [I for I in self.rows_of[rr] if I > k]
+                if not rows:
+                    continue
+                src = rr * self.Pc + kc
+                buf = self.panel[rr][:len(rows)]
+                if self.rank == src:
+                    i0, j = self.ri[rows[0]], self.ci[k]
+                    sub = self.local[i0 * NB:(i0 + len(rows)) * NB, j * NB:(j + 1) * NB]
+                    be.trsm(sub, self.lkk, self.wkk)
+                    buf.copy_(sub.reshape(len(rows), NB, NB))
+                self._bcast(buf, src)
+            # rows of the panel that face my block columns, in increasing J
+            cols = [J for J in self.my_cols if J > k]
+            for n, J in enumerate(cols):
+                rr = J % self.Pr
+                self.pc_buf[n].copy_(self.panel[rr][self.rows_of[rr].index(J) - self._first_after(rr, k)])
+            pcm = self.pc_buf.reshape(-1, NB)
+            # trailing update of my blocks: one GEMM per owned block row
+            mine = [I for I in self.my_rows if I > k]
+            base = self._first_after(self.r, k)
+            for I in mine:
+                ncols = sum(1 for J in cols if J <= I)
+                if ncols == 0:
+                    continue
+                i, j0 = self.ri[I], self.ci[cols[0]]
+                Cm = self.local[i * NB:(i + 1) * NB, j0 * NB:(j0 + ncols) * NB]
+                A = self.panel[self.r][self.rows_of[self.r].index(I) - base]
+                be.gemm(Cm, A, pcm[:ncols * NB], -1.0, 1.0)
+        self.factored = True
+
+    def _first_after(self, rr, k):
+        """index in rows_of[rr] of the first block row > k (the panel buffers start there)"""
+        return sum(1 for I in self.rows_of[rr] if I <= k)
+
+    def logdet(self):
+        """log det K = 2 sum log L_ii (one scalar all-reduce)."""
+        t = self.sumlog.clone()
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return 2.0 * float(t.item())
+
+    # ---- z = L^-1 y and the log marginal likelihood (gp/gp.go:244-253) -----------------
+    def solve_lml(self, y):
+        NB, be, nb = self.NB, self.be, self.nb
+        ypad = be.zeros(nb * NB)
+        ypad[:self.N] = torch.as_tensor(np.asarray(y, dtype=np.float64)).to(ypad.device)
+        zcols = be.zeros(max(1, len(self.my_cols)) * NB)   # z_J for my block columns, in order
+        acc = be.zeros(NB)
+        scratch = be.zeros(NB)
+        zk = be.zeros(NB)
+        ss = be.zeros(1)
+        for k in range(nb):
+            acc.zero_()
+            if k % self.Pr == self.r:
+                ncols = sum(1 for J in self.my_cols if J < k)
+                if ncols:
+                    i = self.ri[k]
+                    be.gemv_sub(self.local[i * NB:(i + 1) * NB, :ncols * NB], zcols[:ncols * NB], acc, scratch)
+            if self.world > 1:
+                self.dist.all_reduce(acc)   # NB doubles; ranks outside the process row add zeros
+            ok = self.owner(k, k)
+            if self.rank == ok:
+                rhs = ypad[k * NB:(k + 1) * NB] + acc
+                be.trsv(self.block(k, k), self.winv_diag[k], rhs, zk)
+            self._bcast(zk, ok)
+            ss += (zk * zk).sum()
+            if k in self.ci:
+                j = self.ci[k]
+                zcols[j * NB:(j + 1) * NB].copy_(zk)
+        quad = float(ss.item())
+        return -0.5 * self.N * math.log(2 * math.pi) - 0.5 * self.logdet() - 0.5 * quad

@@ -162,6 +162,41 @@ gogp_status gogp_timer_stop(gogp_handle* h, double* ms);
 gogp_status gogp_profile_enable(gogp_handle* h, int on);
 gogp_status gogp_profile_read(gogp_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
 
+/* ---- Device-level building blocks for the multi-GPU block-cyclic factorisation ------------
+ * (orchestrated one process per GPU by gogp_b200/dist_chol.py with
+ * torch.distributed/NCCL panel broadcasts).  Every pointer below is a DEVICE pointer on the
+ * handle's device, `stream` is a cudaStream_t (NULL: the handle's own stream), all sizes are
+ * multiples of 128, calls are asynchronous on that stream. */
+
+/* Upload inputs once: X (N x ndim, host) -> the handle's dimension-major device copy. */
+gogp_status gogp_dev_set_inputs(gogp_handle* h, const double* X, int64_t N);
+/* One block of K(X,X)+noise for natural-scale parameters: rows [row0, row0+rows), columns
+ * [col0, col0+cols) into out (leading dimension ld).  diagonal != 0 (row0 == col0, rows == cols):
+ * lower tiles only, noise on the diagonal, identity beyond N; otherwise full rectangle, zero beyond N. */
+gogp_status gogp_dev_cov_block(gogp_handle* h, const double* theta_simil, const double* theta_noise,
+                               int64_t row0, int64_t rows, int64_t col0, int64_t cols, int diagonal,
+                               double* out, int64_t ld, void* stream);
+/* Cholesky of an n x n block in place (lower) + inverses of its 128 x 128 diagonal tiles into winv
+ * ([n/128][128][128]); *info (device int, zero it first) gets base+1-based index of a bad pivot. */
+gogp_status gogp_dev_potrf(gogp_handle* h, double* A, int64_t ld, int64_t n, double* winv, int* info, int base,
+                           void* stream);
+/* B (m x n, ldb) <- B L^-T with the factored block L (ldl) and its tile inverses. */
+gogp_status gogp_dev_trsm(gogp_handle* h, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl,
+                          int64_t n, const double* winv, void* stream);
+/* C = beta C + alpha A B^T (m x n, inner k); lower != 0: only tiles on or below the diagonal. */
+gogp_status gogp_dev_gemm(gogp_handle* h, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
+                          int64_t ldb, int64_t m, int64_t n, int64_t k, double alpha, double beta, int lower,
+                          void* stream);
+/* out[0] = sum_{i < nvalid} log L_ii of a factored block. */
+gogp_status gogp_dev_sumlogdiag(gogp_handle* h, const double* L, int64_t ld, int64_t nvalid, double* out,
+                                void* stream);
+/* Block forward-substitution pieces for z = L^-1 y:  acc[r] -= sum_c B[r][c] v[c]  (rows x cols block),
+ * and  z = Lkk^-1 rhs  for one factored diagonal block (rhs is destroyed; n multiple of 128). */
+gogp_status gogp_dev_gemv_sub(gogp_handle* h, const double* B, int64_t ld, int64_t rows, int64_t cols,
+                              const double* v, double* acc, double* scratch, void* stream);
+gogp_status gogp_dev_trsv(gogp_handle* h, const double* L, int64_t ld, const double* winv, double* rhs, double* z,
+                          int64_t n, void* stream);
+
 /* Test/diagnostic access to device state: what = 0 K (before factorisation is
  * not kept; returns the factor buffer), 1 L, 2 K^-1 (after gogp_gradient).
  * out is N x N row-major, lower triangle valid, upper mirrored. */

@@ -1,0 +1,155 @@
+"""The 2D block-cyclic Cholesky orchestration (gogp_b200/dist_chol.py) on CPU:
+gloo ranks + a NumPy compute backend defined here (test infrastructure), against the
+oracle's log marginal likelihood.  On the GPU box the same orchestration runs with the
+CUDA backend (tests/test_gpu_dist.py, tools/dist_bench.py)."""
+import math
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import torch
+import torch.multiprocessing as mp
+
+from tests.conftest import ROOT
+
+NAME, N, NB = "c5_matern4", 700, 128
+
+
+class NumpyBlocks:
+    """Same interface as dist_chol.CudaBlocks, NumPy arithmetic on torch CPU tensors."""
+
+    def __init__(self, oracle_simil, oracle_noise):
+        self.simil, self.noise, self.bad = oracle_simil, oracle_noise, 0
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float64)
+
+    def empty(self, *shape):
+        return torch.full(tuple(shape), float("nan"), dtype=torch.float64)  # poison: nothing may depend on it
+
+    def set_inputs(self, X):
+        self.X = np.asarray(X, dtype=np.float64)
+
+    def cov_block(self, ts, tn, row0, rows, col0, cols, diagonal, out):
+        from oracle.gp import _noise, _pairs
+        n = len(self.X)
+        blk = np.zeros((rows, cols))
+        r1, c1 = min(n, row0 + rows), min(n, col0 + cols)
+        if r1 > row0 and c1 > col0:
+            k, _ = _pairs(self.simil, np.asarray(ts), self.X[col0:c1], self.X[row0:r1], "none")
+            blk[:r1 - row0, :c1 - col0] = k.T
+        if diagonal:
+            nv, _ = _noise(self.noise, np.asarray(tn), self.X[row0:r1], "none")
+            for i in range(rows):
+                blk[i, i] = blk[i, i] + nv[i] if row0 + i < n else 1.0
+            blk = np.tril(blk) + np.triu(np.full((rows, cols), np.nan), 1)  # the device builds lower tiles only
+        out.copy_(torch.from_numpy(blk))
+
+    def potrf(self, A, winv, base):
+        a = np.tril(A.numpy())
+        a = a + np.tril(a, -1).T
+        try:
+            L = np.linalg.cholesky(a)
+        except np.linalg.LinAlgError:
+            self.bad = base + 1
+            L = np.eye(len(a))
+        A.copy_(torch.from_numpy(L))
+        for t in range(len(a) // 128):
+            blk = L[t * 128:(t + 1) * 128, t * 128:(t + 1) * 128]
+            winv[t].copy_(torch.from_numpy(np.linalg.inv(blk)))
+
+    def trsm(self, B, L, winv):
+        x = sla.solve_triangular(np.tril(L.numpy()), B.numpy().T, lower=True).T
+        B.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+
+    def gemm(self, Cm, A, B, alpha, beta, lower=False):
+        Cm.copy_(beta * Cm + alpha * (A @ B.T))
+
+    def sumlogdiag(self, Lb, nvalid, out2):
+        out2[0] = float(np.sum(np.log(np.diag(Lb.numpy())[:max(nvalid, 0)])))
+
+    def gemv_sub(self, B, v, acc, scratch):
+        acc -= B @ v
+
+    def trsv(self, Lb, winv, rhs, z):
+        z.copy_(torch.from_numpy(sla.solve_triangular(np.tril(Lb.numpy()), rhs.numpy(), lower=True)))
+
+    def bad_pivot(self):
+        return self.bad
+
+
+def _problem():
+    from tests import cases
+    X, y, logt = cases.synth(NAME, N, seed=21)
+    return X, y, logt
+
+
+def _run(rank, world, grid, port, out):
+    sys.path.insert(0, ROOT)
+    from gogp_b200.dist_chol import BlockCyclicCholesky
+    from tests import cases
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, y, logt = _problem()
+    _, _, _, osim, onoise = cases.CASES[NAME]
+    be = NumpyBlocks(osim, onoise)
+    be.set_inputs(X)
+    ch = BlockCyclicCholesky(be, N, NB, rank, world, grid, dist)
+    th = np.exp(logt)
+    ch.build(th[:osim.ntheta], th[osim.ntheta:])
+    ch.factor()
+    lml = ch.solve_lml(y)
+    res = np.array([ch.logdet(), lml, float(be.bad_pivot())])
+    if out is not None:
+        np.save(os.path.join(out, "r%d.npy" % rank), res)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return res
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle():
+    from tests import cases
+    X, y, logt = _problem()
+    g = cases.make_oracle_gp(NAME)
+    g.X, g.Y = X, y
+    lml = g.observe(logt.copy())
+    return 2.0 * float(np.sum(np.log(np.diag(g.L)))), lml
+
+
+def test_default_grids():
+    from gogp_b200.dist_chol import default_grid
+    assert [default_grid(w) for w in (1, 2, 4, 8)] == [(1, 1), (2, 1), (2, 2), (4, 2)]
+
+
+def test_single_rank_matches_oracle():
+    logdet, lml = _oracle()
+    res = _run(0, 1, (1, 1), 0, None)
+    assert res[2] == 0
+    assert abs(res[0] - logdet) < 1e-9 * abs(logdet)
+    assert abs(res[1] - lml) < 1e-9 * max(abs(lml), N)
+
+
+@pytest.mark.parametrize("world,grid", [(2, (2, 1)), (2, (1, 2)), (4, (2, 2))])
+def test_gloo_ranks_match_oracle(tmp_path, world, grid):
+    logdet, lml = _oracle()
+    mp.spawn(_run, args=(world, grid, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = np.load(tmp_path / ("r%d.npy" % r))
+        assert res[2] == 0
+        assert abs(res[0] - logdet) < 1e-9 * abs(logdet), (r, res, logdet)
+        assert abs(res[1] - lml) < 1e-9 * max(abs(lml), N), (r, res, lml)

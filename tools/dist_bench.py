@@ -1,0 +1,115 @@
+"""Block-cyclic Cholesky across the GPUs of one box (BASELINE configs[4]).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 \
+      --master-port 29511 tools/dist_bench.py --n 131072 --nb 2048 [--check]
+
+Prints one JSON line from rank 0: build / factor / solve device times (CUDA events on
+the compute stream, max over ranks), Cholesky TFLOP/s (N^3/3 over all GPUs) and, with
+--check (N <= 32768), the difference to the single-GPU path of the same library.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gogp_b200 import GP, kernel as k  # noqa: E402
+from gogp_b200.dist_chol import BlockCyclicCholesky, CudaBlocks, default_grid  # noqa: E402
+
+NDIM = 4
+
+
+def kernel_c5():
+    e = k.Param(0)
+    for d in range(NDIM):
+        e = e * k.Matern32.Of(l=1 + d, dim=d)
+    return e, k.UniformNoise
+
+
+def synth(N, seed=0):
+    """x ~ U(0,8)^4, y = sum sin(x_d) + 0.1 N(0,1) normalised, sigma = 0.1."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0.0, 8.0, size=(N, NDIM))
+    y = np.sin(X).sum(axis=1) + 0.1 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    logt = np.zeros(NDIM + 2)
+    logt[NDIM + 1] = math.log(0.1)
+    return X, y, logt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=131072)
+    ap.add_argument("--nb", type=int, default=2048)
+    ap.add_argument("--pr", type=int, default=0)
+    ap.add_argument("--pc", type=int, default=0)
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--reps", type=int, default=1)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    grid = (a.pr, a.pc) if a.pr and a.pc else default_grid(world)
+    simil, noise = kernel_c5()
+    X, y, logt = synth(a.n)
+    th = np.exp(logt)
+    be = CudaBlocks(simil, noise, NDIM, local)
+    be.set_inputs(X)
+    ch = BlockCyclicCholesky(be, a.n, a.nb, rank, world, grid, dist if world > 1 else None)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    res = []
+    for rep in range(a.reps + 1):  # first pass warms up (allocations, NCCL channels)
+        l0 = be.launches()
+        t_build, _ = timed(lambda: ch.build(th[:NDIM + 1], th[NDIM + 1:]))
+        t_fac, _ = timed(ch.factor)
+        t_sol, lml = timed(lambda: ch.solve_lml(y))
+        res.append((t_build, t_fac, t_sol, lml, be.launches() - l0))
+    t_build, t_fac, t_sol, lml, launches = res[-1]
+    bad = be.bad_pivot()
+    out = {
+        "workload": "configs[4]: synthetic 4-D Matern32 + noise, block-cyclic Cholesky", "N": a.n, "NB": a.nb,
+        "n_gpus": world, "grid": list(grid), "build_ms": t_build, "factor_ms": t_fac, "solve_ms": t_sol,
+        "cholesky_tflops_total": a.n ** 3 / 3 / (t_fac * 1e-3) / 1e12,
+        "cholesky_tflops_per_gpu": a.n ** 3 / 3 / (t_fac * 1e-3) / 1e12 / world,
+        "lml": lml, "bad_pivot": bad, "launches_rank0": launches,
+        "mem_gb_rank0": torch.cuda.max_memory_allocated() / 1e9,
+    }
+    if a.check and rank == 0:
+        g = GP(NDim=NDIM, Simil=simil, Noise=noise, Device=local)
+        g.X, g.Y = X, y
+        ref = g.Observe(logt.copy())
+        out["single_gpu_lml"] = ref
+        out["rel_diff"] = abs(lml - ref) / max(abs(ref), a.n)
+        g.close()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    be.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
