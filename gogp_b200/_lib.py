@@ -93,7 +93,7 @@ def lib():
     L.gogp_debug_gemm.argtypes = [H, C.c_int64, C.c_int64, C.c_int, C.c_int, dp]
     L.gogp_debug_gemm.restype = C.c_int
     vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double  # device pointers travel as integers
-    L.gogp_dev_set_inputs.argtypes = [H, dp, i64]
+    L.gogp_dev_set_inputs.argtypes = [H, dp, i64, i64]
     L.gogp_dev_cov_block.argtypes = [H, dp, dp, i64, i64, i64, i64, C.c_int, vp, i64, vp]
     L.gogp_dev_potrf.argtypes = [H, vp, i64, i64, vp, vp, C.c_int, vp]
     L.gogp_dev_trsm.argtypes = [H, vp, i64, i64, vp, i64, i64, vp, vp]

@@ -663,13 +663,14 @@ gogp_status gogp_debug_gemm(gogp_handle* h, int64_t n, int64_t k, int mode, int 
 
 // ---- device-level building blocks (multi-GPU block-cyclic factorisation) ---------------------
 static inline cudaStream_t pick_stream(gogp_handle* h, void* stream) {
-    return stream ? (cudaStream_t)stream : h->stream;
+    (void)h;
+    return (cudaStream_t)stream;  // NULL is the legacy default stream (torch's default current stream)
 }
 
-gogp_status gogp_dev_set_inputs(gogp_handle* h, const double* X, int64_t N) {
-    if (!h || !X || N <= 0) return GOGP_BAD_ARGUMENT;
+gogp_status gogp_dev_set_inputs(gogp_handle* h, const double* X, int64_t N, int64_t block) {
+    if (!h || !X || N <= 0 || block <= 0 || block % TILE) return GOGP_BAD_ARGUMENT;
     CK(cudaSetDevice(h->dev));
-    const int64_t Npad = pad_tile(N);
+    const int64_t Npad = ((N + block - 1) / block) * block;
     free_dev(h->dXraw);
     free_dev(h->dXt);
     h->cap = 0;  // the single-GPU buffers are not kept alongside

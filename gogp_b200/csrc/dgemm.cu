@@ -71,8 +71,16 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_nt_kernel(const Gemm
         lower_tile(blockIdx.x / RATIO, ti, tg);
         tj = tg * RATIO + blockIdx.x % RATIO;
     } else {
-        ti = blockIdx.x / g.tn;
-        tj = blockIdx.x % g.tn;
+        // grouped rasterisation: walk GROUP_M row tiles column by column, so the CTAs resident at
+        // any time share a few A row-panels and a few B column-panels through L2 instead of
+        // streaming the whole B operand from HBM once per row tile
+        constexpr int GROUP_M = 16;
+        const int per_group = GROUP_M * g.tn;
+        const int gid = blockIdx.x / per_group, rem = blockIdx.x % per_group;
+        const int first = gid * GROUP_M;
+        const int gsz = (g.tm - first) < GROUP_M ? (g.tm - first) : GROUP_M;
+        ti = first + rem % gsz;
+        tj = rem / gsz;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WN, wn = warp % WN;

@@ -61,9 +61,9 @@ class CudaBlocks:
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float64, device=self.device)
 
-    def set_inputs(self, X):
+    def set_inputs(self, X, block=128):
         X = np.ascontiguousarray(X, dtype=np.float64)
-        self._ck(self.L.gogp_dev_set_inputs(self.h, self._lib.dptr(X.reshape(-1)), X.shape[0]))
+        self._ck(self.L.gogp_dev_set_inputs(self.h, self._lib.dptr(X.reshape(-1)), X.shape[0], block))
 
     def cov_block(self, theta_s, theta_n, row0, rows, col0, cols, diagonal, out):
         ts = np.ascontiguousarray(theta_s, dtype=np.float64)
@@ -95,6 +95,25 @@ class CudaBlocks:
     def trsv(self, Lb, winv, rhs, z):
         self._ck(self.L.gogp_dev_trsv(self.h, self._p(Lb), Lb.stride(0), self._p(winv), rhs.data_ptr(),
                                       z.data_ptr(), Lb.shape[0], self._stream()))
+
+    # look-ahead plumbing: run a batch of launches on a side stream, ordered after the
+    # current point of the main (current) stream; wait_side() orders the main stream after it
+    def side(self, fn):
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(self.device)
+            self._side_done = None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            fn()
+            self._side_done = torch.cuda.Event()
+            self._side_done.record(self._side)
+
+    def wait_side(self):
+        if getattr(self, "_side_done", None) is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._side_done)
+            self._side_done = None
 
     def bad_pivot(self):
         return int(self.info.item())
@@ -130,10 +149,12 @@ class BlockCyclicCholesky:
         self.ri = {I: i for i, I in enumerate(self.my_rows)}
         self.ci = {J: j for j, J in enumerate(self.my_cols)}
         self.local = backend.empty(max(1, len(self.my_rows)) * NB, max(1, len(self.my_cols)) * NB)
-        # the whole panel of the current step, organised by process row
+        # the whole panel of a step, organised by process row; two generations, because the
+        # bulk of step k's trailing update (side stream) overlaps step k+1's panel work
         self.rows_of = [[I for I in range(self.nb) if I % self.Pr == rr] for rr in range(self.Pr)]
-        self.panel = [backend.empty(max(1, len(self.rows_of[rr])), NB, NB) for rr in range(self.Pr)]
-        self.pc_buf = backend.empty(max(1, len(self.my_cols)), NB, NB)
+        self.panels = [[backend.empty(max(1, len(self.rows_of[rr])), NB, NB) for rr in range(self.Pr)]
+                       for _ in range(2)]
+        self.pc_bufs = [backend.empty(max(1, len(self.my_cols)), NB, NB) for _ in range(2)]
         self.lkk = backend.empty(NB, NB)
         self.wkk = backend.empty(NB // 128, 128, 128)
         self.winv_diag = {}   # tile inverses of the diagonal blocks this rank owns (for the solve)
@@ -167,6 +188,7 @@ class BlockCyclicCholesky:
         self.sumlog.zero_()
         for k in range(self.nb):
             ok = self.owner(k, k)
+            panel, pc_buf = self.panels[k % 2], self.pc_bufs[k % 2]
             if self.rank == ok:
                 d = self.block(k, k)
                 w = be.empty(NB // 128, 128, 128)
@@ -187,7 +209,7 @@ class BlockCyclicCholesky:
                 if not rows:
                     continue
                 src = rr * self.Pc + kc
-                buf = self.panel[rr][:len(rows)]
+                buf = panel[rr][:len(rows)]
                 if self.rank == src:
                     i0, j = self.ri[rows[0]], self.ci[k]
                     sub = self.local[i0 * NB:(i0 + len(rows)) * NB, j * NB:(j + 1) * NB]
@@ -198,19 +220,37 @@ class BlockCyclicCholesky:
             cols = [J for J in self.my_cols if J > k]
             for n, J in enumerate(cols):
                 rr = J % self.Pr
-                self.pc_buf[n].copy_(self.panel[rr][self.rows_of[rr].index(J) - self._first_after(rr, k)])
-            pcm = self.pc_buf.reshape(-1, NB)
-            # trailing update of my blocks: one GEMM per owned block row
+                pc_buf[n].copy_(panel[rr][self.rows_of[rr].index(J) - self._first_after(rr, k)])
+            pcm = pc_buf.reshape(-1, NB)
             mine = [I for I in self.my_rows if I > k]
+            if not mine or not cols:
+                continue
             base = self._first_after(self.r, k)
-            for I in mine:
-                ncols = sum(1 for J in cols if J <= I)
-                if ncols == 0:
-                    continue
-                i, j0 = self.ri[I], self.ci[cols[0]]
-                Cm = self.local[i * NB:(i + 1) * NB, j0 * NB:(j0 + ncols) * NB]
-                A = self.panel[self.r][self.rows_of[self.r].index(I) - base]
-                be.gemm(Cm, A, pcm[:ncols * NB], -1.0, 1.0)
+            mypanel = panel[self.r][:len(mine)].reshape(-1, NB)   # my block rows > k, contiguous
+            i0 = self.ri[mine[0]]
+            # the previous step's bulk update (side stream) touches the same blocks: order after it
+            be.wait_side()
+            first = 0
+            if cols[0] == k + 1:
+                # look-ahead: block column k+1 first, on the main stream -- it is all the next
+                # step's factor / panel solve / broadcasts depend on
+                j = self.ci[k + 1]
+                be.gemm(self.local[i0 * NB:(i0 + len(mine)) * NB, j * NB:(j + 1) * NB], mypanel, pcm[:NB], -1.0, 1.0)
+                first = 1
+
+            def bulk(first=first, mine=mine, cols=cols, panel=panel, pcm=pcm, base=base):
+                # the rest of my trailing blocks: one GEMM per owned block row
+                for I in mine:
+                    ncols = sum(1 for J in cols if J <= I)
+                    if ncols <= first:
+                        continue
+                    i, j0 = self.ri[I], self.ci[cols[first]]
+                    Cm = self.local[i * NB:(i + 1) * NB, j0 * NB:(j0 + ncols - first) * NB]
+                    A = panel[self.r][self.rows_of[self.r].index(I) - base]
+                    be.gemm(Cm, A, pcm[first * NB:ncols * NB], -1.0, 1.0)
+
+            be.side(bulk)
+        be.wait_side()
         self.factored = True
 
     def _first_after(self, rr, k):

@@ -165,11 +165,12 @@ gogp_status gogp_profile_read(gogp_handle* h, double* gemm_ms, double* gemm_flop
 /* ---- Device-level building blocks for the multi-GPU block-cyclic factorisation ------------
  * (orchestrated one process per GPU by gogp_b200/dist_chol.py with
  * torch.distributed/NCCL panel broadcasts).  Every pointer below is a DEVICE pointer on the
- * handle's device, `stream` is a cudaStream_t (NULL: the handle's own stream), all sizes are
+ * handle's device, `stream` is the caller's cudaStream_t (NULL: the legacy default stream), all sizes are
  * multiples of 128, calls are asynchronous on that stream. */
 
-/* Upload inputs once: X (N x ndim, host) -> the handle's dimension-major device copy. */
-gogp_status gogp_dev_set_inputs(gogp_handle* h, const double* X, int64_t N);
+/* Upload inputs once: X (N x ndim, host) -> the handle's dimension-major device copy, zero-padded
+ * to a multiple of `block` (a multiple of 128: the distribution block size). */
+gogp_status gogp_dev_set_inputs(gogp_handle* h, const double* X, int64_t N, int64_t block);
 /* One block of K(X,X)+noise for natural-scale parameters: rows [row0, row0+rows), columns
  * [col0, col0+cols) into out (leading dimension ld).  diagonal != 0 (row0 == col0, rows == cols):
  * lower tiles only, noise on the diagonal, identity beyond N; otherwise full rectangle, zero beyond N. */

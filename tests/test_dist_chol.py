@@ -30,7 +30,7 @@ class NumpyBlocks:
     def empty(self, *shape):
         return torch.full(tuple(shape), float("nan"), dtype=torch.float64)  # poison: nothing may depend on it
 
-    def set_inputs(self, X):
+    def set_inputs(self, X, block=128):
         self.X = np.asarray(X, dtype=np.float64)
 
     def cov_block(self, ts, tn, row0, rows, col0, cols, diagonal, out):
@@ -76,6 +76,12 @@ class NumpyBlocks:
 
     def trsv(self, Lb, winv, rhs, z):
         z.copy_(torch.from_numpy(sla.solve_triangular(np.tril(Lb.numpy()), rhs.numpy(), lower=True)))
+
+    def side(self, fn):
+        fn()
+
+    def wait_side(self):
+        pass
 
     def bad_pivot(self):
         return self.bad

@@ -18,7 +18,7 @@ def test_block_cyclic_single_rank_matches_oracle(name, N, NB):
     og.X, og.Y = X, y
     ref = og.observe(logt.copy())
     be = CudaBlocks(ds, dn, ndim, 0)
-    be.set_inputs(X)
+    be.set_inputs(X, NB)
     ch = BlockCyclicCholesky(be, N, NB)
     th = np.exp(logt)
     nts = ds.NTheta()

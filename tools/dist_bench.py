@@ -1,7 +1,7 @@
 """Block-cyclic Cholesky across the GPUs of one box (BASELINE configs[4]).
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 \
-      --master-port 29511 tools/dist_bench.py --n 131072 --nb 2048 [--check]
+      --master-port 29511 tools/dist_bench.py --size 131072 --block 2048 [--check]
 
 Prints one JSON line from rank 0: build / factor / solve device times (CUDA events on
 the compute stream, max over ranks), Cholesky TFLOP/s (N^3/3 over all GPUs) and, with
@@ -44,8 +44,8 @@ def synth(N, seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=131072)
-    ap.add_argument("--nb", type=int, default=2048)
+    ap.add_argument("--size", dest="n", type=int, default=131072)
+    ap.add_argument("--block", dest="nb", type=int, default=2048)
     ap.add_argument("--pr", type=int, default=0)
     ap.add_argument("--pc", type=int, default=0)
     ap.add_argument("--check", action="store_true")
@@ -62,7 +62,7 @@ def main():
     X, y, logt = synth(a.n)
     th = np.exp(logt)
     be = CudaBlocks(simil, noise, NDIM, local)
-    be.set_inputs(X)
+    be.set_inputs(X, a.nb)
     ch = BlockCyclicCholesky(be, a.n, a.nb, rank, world, grid, dist if world > 1 else None)
 
     def timed(fn):
