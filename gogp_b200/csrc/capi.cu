@@ -20,6 +20,7 @@ namespace {
 
 constexpr double kNoNoise = 1e-5;  // gp/gp.go:43
 constexpr int64_t kProduceChunk = 8192;
+constexpr int64_t kOutOfPlaceRows = 2048;
 
 inline int64_t pad_tile(int64_t n) { return n <= 0 ? 0 : ((n + TILE - 1) / TILE) * TILE; }
 
@@ -81,11 +82,23 @@ struct CudaBackend {
     int* info;
     int64_t* launches;
     GemmProfile* prof;
+    double* scratch = nullptr;   // [scratch_rows][128]: out-of-place target of large in-place solves
+    int64_t scratch_rows = 0;
     void gemm(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m, int64_t n,
               int64_t k, double alpha, double beta, int mode, double* cdiag) {
         const bool p = prof && prof->on;
         if (p) cudaEventRecord(prof->next(), s);
-        launch_dgemm_nt(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s);
+        if ((mode & GEMM_INPLACE) && scratch && m >= kOutOfPlaceRows && m <= scratch_rows && n == TILE) {
+            // X = B Winv^T for many rows: the faster 2-CTA/SM shape cannot run in place (two CTAs
+            // would share rows), so it writes to scratch and a copy brings the block back.  Its
+            // 90 KB CTAs also interleave with a concurrent bulk GEMM, which the 160 KB in-place
+            // shape cannot (it would wait for an entire SM to drain).
+            launch_dgemm_nt(scratch, TILE, A, lda, B, ldb, m, n, k, alpha, 0.0, GEMM_FULL, nullptr, s);
+            launch_copy_block(C, ldc, scratch, TILE, m, TILE, s);
+            ++*launches;
+        } else {
+            launch_dgemm_nt(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s);
+        }
         if (p) {
             cudaEventRecord(prof->next(), s);
             prof->flops += gemm_flops(m, n, k, mode);
@@ -123,6 +136,8 @@ struct gogp_handle {
     double *dB = nullptr, *dDg = nullptr, *dPartial = nullptr;
     double *dAlpha = nullptr, *dW = nullptr, *dZ = nullptr, *dRed = nullptr, *dGx = nullptr;
     int* dInfo = nullptr;
+    double* dScr = nullptr;  // [scrRows][128] scratch of the out-of-place block solves
+    int64_t scrRows = 0;
     double* hPin = nullptr;  // pinned staging for small results
     int64_t hPinCap = 0;
     // Produce scratch
@@ -169,7 +184,20 @@ gogp_status ensure_pin(gogp_handle* h, int64_t n) {
     return GOGP_OK;
 }
 
+gogp_status ensure_scratch(gogp_handle* h, int64_t rows) {
+    if (rows <= h->scrRows) return GOGP_OK;
+    free_dev(h->dScr);
+    h->scrRows = 0;
+    CK(cudaMalloc(&h->dScr, (size_t)rows * TILE * sizeof(double)));
+    h->scrRows = rows;
+    return GOGP_OK;
+}
+
 gogp_status ensure_capacity(gogp_handle* h, int64_t Npad) {
+    {
+        gogp_status st = ensure_scratch(h, Npad);
+        if (st != GOGP_OK) return st;
+    }
     if (Npad <= h->cap) return GOGP_OK;
     free_dev(h->dXraw); free_dev(h->dXt); free_dev(h->dY); free_dev(h->dA); free_dev(h->dWinv);
     free_dev(h->dAlpha); free_dev(h->dW); free_dev(h->dZ); free_dev(h->dGx);
@@ -254,7 +282,7 @@ gogp_status absorb(gogp_handle* h) {
     ++h->launches;
     CK(cudaEventRecord(h->ev[1], s));
 
-    CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
+    CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
     Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
     bl.potrf(0, Npad);
     CK(cudaEventRecord(h->ev[2], s));
@@ -345,7 +373,7 @@ void gogp_destroy(gogp_handle* h) {
     free_dev(h->dXraw); free_dev(h->dXt); free_dev(h->dY); free_dev(h->dA); free_dev(h->dWinv);
     free_dev(h->dAlpha); free_dev(h->dW); free_dev(h->dZ); free_dev(h->dGx);
     free_dev(h->dB); free_dev(h->dDg); free_dev(h->dPartial); free_dev(h->dRed);
-    free_dev(h->dZraw); free_dev(h->dZt); free_dev(h->dBt); free_dev(h->dPv);
+    free_dev(h->dZraw); free_dev(h->dZt); free_dev(h->dBt); free_dev(h->dPv); free_dev(h->dScr);
     if (h->dInfo) cudaFree(h->dInfo);
     if (h->hPin) cudaFreeHost(h->hPin);
     for (auto& ev : h->ev)
@@ -434,7 +462,7 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
 
     CK(cudaEventRecord(h->ev[0], s));
     if (!h->have_kinv) {
-        CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
+        CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
         Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
         bl.trtri_t(h->dB, 0, Npad);
         bl.lauum(h->dB, h->dDg, Npad);
@@ -520,7 +548,7 @@ gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu,
         if (N > 0) {
             launch_cov_cross(prog, h->dXt, N, Npad, h->dZt, mc, mpad, D, h->dBt, s);
             launch_row_reduce(h->dBt, Npad, mc, Npad, h->dAlpha, dmu, s);  // mean = Kstar^T alpha, gp/gp.go:335
-            CudaBackend be{s, h->dInfo, &h->launches, &h->prof};
+            CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
             Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
             bl.trsm(h->dBt, Npad, mpad, 0, Npad);                        // V^T = Kstar^T L^-T
             launch_row_reduce(h->dBt, Npad, mc, Npad, nullptr, dss, s);  // diag(Kstar^T K^-1 Kstar)
@@ -727,7 +755,7 @@ gogp_status gogp_dev_potrf(gogp_handle* h, double* A, int64_t ld, int64_t n, dou
     struct Shifted : CudaBackend {
         int shift;
         void potrf_leaf(double* At, int64_t l, double* w, int b) { CudaBackend::potrf_leaf(At, l, w, b + shift); }
-    } be{{pick_stream(h, stream), info, &h->launches, &h->prof}, base};
+    } be{{pick_stream(h, stream), info, &h->launches, &h->prof, nullptr, 0}, base};
     Blocked<Shifted> bl{be, A, ld, winv, rl_max(), cols_max()};
     bl.potrf(0, n);
     CK(cudaGetLastError());
@@ -738,7 +766,11 @@ gogp_status gogp_dev_trsm(gogp_handle* h, double* B, int64_t ldb, int64_t m, con
                           const double* winv, void* stream) {
     if (!h || !B || !L || !winv || m <= 0 || n <= 0 || m % TILE || n % TILE) return GOGP_BAD_ARGUMENT;
     CK(cudaSetDevice(h->dev));
-    CudaBackend be{pick_stream(h, stream), h->dInfo, &h->launches, &h->prof};
+    {
+        gogp_status st = ensure_scratch(h, m);
+        if (st != GOGP_OK) return st;
+    }
+    CudaBackend be{pick_stream(h, stream), h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
     Blocked<CudaBackend> bl{be, const_cast<double*>(L), ldl, const_cast<double*>(winv), rl_max(), cols_max()};
     bl.trsm(B, ldb, m, 0, n);
     CK(cudaGetLastError());
@@ -751,7 +783,7 @@ gogp_status gogp_dev_gemm(gogp_handle* h, double* C, int64_t ldc, const double* 
     if (!h || !C || !A || !B || m <= 0 || n <= 0 || k <= 0 || m % TILE || n % TILE || k % TILE) return GOGP_BAD_ARGUMENT;
     if (lower && m != n) return fail(h, GOGP_BAD_ARGUMENT, "lower needs a square C");
     CK(cudaSetDevice(h->dev));
-    CudaBackend be{pick_stream(h, stream), h->dInfo, &h->launches, &h->prof};
+    CudaBackend be{pick_stream(h, stream), h->dInfo, &h->launches, &h->prof, nullptr, 0};
     be.gemm(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, lower ? GEMM_LOWER : GEMM_FULL, nullptr);
     CK(cudaGetLastError());
     return GOGP_OK;

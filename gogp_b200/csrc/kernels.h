@@ -71,6 +71,9 @@ void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t
 // rhs (Npad) is destroyed; out must not alias it.
 void launch_trsv_lower(const double* L, int64_t ld, const double* winv, double* rhs, double* out, int64_t Npad,
                        bool transposed, cudaStream_t s, int64_t* launches);
+// dst[r][c] = src[r][c] for a rows x cols block (cols even, 16-byte aligned rows)
+void launch_copy_block(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols,
+                       cudaStream_t s);
 // y += a x
 void launch_axpy(double* y, const double* x, double a, int64_t n, cudaStream_t s);
 // v[i] = value for i in [0, n)

@@ -296,6 +296,20 @@ void launch_axpy(double* y, const double* x, double a, int64_t n, cudaStream_t s
     if (n > 0) axpy_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(y, x, a, n);
 }
 
+__global__ void copy_block_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
+                                  int64_t rows, int cols2) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= rows * cols2) return;
+    const int64_t r = i / cols2;
+    const int c = (int)(i - r * cols2) * 2;
+    *reinterpret_cast<double2*>(dst + r * ldd + c) = *reinterpret_cast<const double2*>(src + r * lds + c);
+}
+void launch_copy_block(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols,
+                       cudaStream_t s) {
+    const int64_t n = rows * (cols / 2);
+    if (n > 0) copy_block_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(dst, ldd, src, lds, rows, (int)(cols / 2));
+}
+
 void launch_fill(double* v, int64_t n, double value, cudaStream_t s) {
     if (n > 0) fill_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(v, n, value, 0);
 }

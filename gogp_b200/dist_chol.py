@@ -183,23 +183,27 @@ class BlockCyclicCholesky:
         self.factored = False
 
     # ---- factor ---------------------------------------------------------------------
-    def factor(self):
+    def _factor_diag(self, k):
+        """Owner of (k, k): factor the block, keep its tile inverses, stage it for the broadcast."""
+        if self.rank != self.owner(k, k):
+            return
+        NB, be = self.NB, self.be
+        d = self.block(k, k)
+        w = be.empty(NB // 128, 128, 128)
+        be.potrf(d, w, k * NB)
+        be.sumlogdiag(d, min(NB, self.N - k * NB), self.logdet2)
+        self.sumlog += self.logdet2[:1]
+        self.winv_diag[k] = w
+        self.lkk.copy_(d)
+        self.wkk.copy_(w)
+
+    def factor(self, lookahead=True):
         NB, be = self.NB, self.be
         self.sumlog.zero_()
-        for k in range(self.nb):
+        self._factor_diag(0)
+        for k in range(self.nb - 1):
             ok = self.owner(k, k)
             panel, pc_buf = self.panels[k % 2], self.pc_bufs[k % 2]
-            if self.rank == ok:
-                d = self.block(k, k)
-                w = be.empty(NB // 128, 128, 128)
-                be.potrf(d, w, k * NB)
-                be.sumlogdiag(d, min(NB, self.N - k * NB), self.logdet2)
-                self.sumlog += self.logdet2[:1]
-                self.winv_diag[k] = w
-                self.lkk.copy_(d)
-                self.wkk.copy_(w)
-            if k == self.nb - 1:
-                break
             self._bcast(self.lkk, ok)
             self._bcast(self.wkk, ok)
             # panel solve on the ranks of process column k mod Pc, then whole-panel broadcast
@@ -223,20 +227,22 @@ class BlockCyclicCholesky:
                 pc_buf[n].copy_(panel[rr][self.rows_of[rr].index(J) - self._first_after(rr, k)])
             pcm = pc_buf.reshape(-1, NB)
             mine = [I for I in self.my_rows if I > k]
-            if not mine or not cols:
-                continue
-            base = self._first_after(self.r, k)
-            mypanel = panel[self.r][:len(mine)].reshape(-1, NB)   # my block rows > k, contiguous
-            i0 = self.ri[mine[0]]
             # the previous step's bulk update (side stream) touches the same blocks: order after it
             be.wait_side()
             first = 0
-            if cols[0] == k + 1:
+            if mine and cols and cols[0] == k + 1:
                 # look-ahead: block column k+1 first, on the main stream -- it is all the next
                 # step's factor / panel solve / broadcasts depend on
-                j = self.ci[k + 1]
+                mypanel = panel[self.r][:len(mine)].reshape(-1, NB)   # my block rows > k, contiguous
+                i0, j = self.ri[mine[0]], self.ci[k + 1]
                 be.gemm(self.local[i0 * NB:(i0 + len(mine)) * NB, j * NB:(j + 1) * NB], mypanel, pcm[:NB], -1.0, 1.0)
                 first = 1
+            # block (k+1, k+1) is final now: its owner factors it BEFORE queueing the bulk update,
+            # whose CTAs would otherwise keep every SM too full for the 135 KB leaf kernel
+            self._factor_diag(k + 1)
+            if not mine or not cols:
+                continue
+            base = self._first_after(self.r, k)
 
             def bulk(first=first, mine=mine, cols=cols, panel=panel, pcm=pcm, base=base):
                 # the rest of my trailing blocks: one GEMM per owned block row
@@ -249,7 +255,10 @@ class BlockCyclicCholesky:
                     A = panel[self.r][self.rows_of[self.r].index(I) - base]
                     be.gemm(Cm, A, pcm[first * NB:ncols * NB], -1.0, 1.0)
 
-            be.side(bulk)
+            if lookahead:
+                be.side(bulk)
+            else:
+                bulk()
         be.wait_side()
         self.factored = True
 
