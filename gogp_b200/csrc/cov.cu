@@ -150,14 +150,15 @@ void launch_cov_self(const DevProgram& prog, const double* Zt, int64_t M, int64_
 }
 
 // ---- fused gradient trace ----------------------------------------------------------
-// One CTA per lower tile.  A thread owns a column pair and 32 rows; the tile is
-// walked in two chunks of 16 rows (E = 32 elements per thread).  For each product
-// term: phase 1 forms w_e * P_e (W-weighted term value) per element, phase 2 runs
-// over the term's factors and accumulates P_e-weighted log-derivatives into the
-// parameter slots.  dK is never materialised (the reference stores one dense
-// N x N matrix per parameter, gp/gp.go:93-97,158-163).
-constexpr int GT_E = 32;
-constexpr int GT_SLOTS = kMaxTheta + 1;
+// One CTA per lower tile; a thread owns a column pair and 32 rows, walked in chunks of
+// 4 rows (E = 8 elements).  For each product term: phase 1 forms w_e * W_e * P_e (term
+// value weighted by W = alpha alpha^T - K^-1 and by 1 below / 1/2 on the diagonal) per
+// element; phase 2 runs over the term's factors and adds the P-weighted log-derivatives
+// to per-thread accumulators, one shared-memory cell per (parameter slot, thread), so
+// nothing is reduced across threads until the end of the tile.  dK is never
+// materialised (the reference stores one dense N x N matrix per parameter,
+// gp/gp.go:93-97,158-163).  ~70 KB of shared memory -> 3 CTAs per SM.
+constexpr int GT_E = 8;
 
 __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__ DevProgram prog,
                                                          const double* __restrict__ Xt, int64_t ldx,
@@ -171,30 +172,32 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
     uint64_t* bar = reinterpret_cast<uint64_t*>(xc + D * TILE);
     double* pw = reinterpret_cast<double*>(bar + 2);  // [GT_E][256] weighted term values
     double* ww = pw + GT_E * 256;                     // [GT_E][256] weights w_e * W_e
-    double* acc = ww + GT_E * 256;                    // [8 warps][GT_SLOTS]
+    double* acc = ww + GT_E * 256;                    // [ntheta + 1][256] per-thread accumulators
 
     int ti, tj;
     lower_tile(blockIdx.x, ti, tj);
     const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int q = tid; q < 8 * GT_SLOTS; q += 256) acc[q] = 0.0;
-    stage_tiles(xr, xc, bar, Xt, ldx, row0, Xt, ldx, col0, D);  // also a block barrier after acc init
+    const int tid = threadIdx.x;
+    const int nslot = prog.ntheta;  // slot ntheta = trace of W
+    for (int q = 0; q <= nslot; ++q) acc[q * 256 + tid] = 0.0;
+    stage_tiles(xr, xc, bar, Xt, ldx, row0, Xt, ldx, col0, D);
 
     const double* ktile = (ti == tj) ? kdiag + (int64_t)ti * TILE * TILE : kinv + row0 * ld + col0;
     const int64_t kld = (ti == tj) ? TILE : ld;
     const int c0 = 2 * (tid & 63);
     const int ir = tid >> 6;
-    const int nslot = prog.ntheta;  // slot ntheta = trace of W
+    const int64_t gj = col0 + c0;
+    const double aj0 = alpha[gj], aj1 = alpha[gj + 1];
     double trw = 0.0;
 
-    for (int chunk = 0; chunk < 2; ++chunk) {
+    for (int chunk = 0; chunk < 2 * TILE / (4 * GT_E); ++chunk) {
         // weights w_e * W_e of this chunk (1 below the diagonal, 1/2 on it, 0 elsewhere)
-#pragma unroll 4
+#pragma unroll
         for (int e = 0; e < GT_E; e += 2) {
-            const int r = chunk * 64 + (e >> 1) * 4 + ir;
-            const int64_t gi = row0 + r, gj = col0 + c0;
+            const int r = (chunk * (GT_E / 2) + (e >> 1)) * 4 + ir;
+            const int64_t gi = row0 + r;
             const double2 kv = *reinterpret_cast<const double2*>(ktile + (int64_t)r * kld + c0);
-            const double ai = alpha[gi], aj0 = alpha[gj], aj1 = alpha[gj + 1];
+            const double ai = alpha[gi];
             double w0 = 0.0, w1 = 0.0;
             if (gi < N && gj < N && gi >= gj) {
                 const double W = ai * aj0 - kv.x;
@@ -221,46 +224,40 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
             const int fb = prog.fbeg[t], fe = prog.fbeg[t + 1];
             // phase 1: weighted term values
             for (int e = 0; e < GT_E; ++e) {
-                const int r = chunk * 64 + (e >> 1) * 4 + ir;
+                const int r = (chunk * (GT_E / 2) + (e >> 1)) * 4 + ir;
                 const int c = c0 + (e & 1);
                 auto xa = [&](int d) { return xc[d * TILE + c]; };
                 auto xb = [&](int d) { return xr[d * TILE + r]; };
-                pw[e * 256 + tid] = ww[e * 256 + tid] * term_value(prog, t, xa, xb);
+                const double w = ww[e * 256 + tid];
+                pw[e * 256 + tid] = (w != 0.0) ? w * term_value(prog, t, xa, xb) : 0.0;
             }
             // phase 2: per-factor log-derivatives
             for (int fi = fb; fi < fe; ++fi) {
                 const DevFactor& f = prog.f[fi];
                 double s0 = 0.0, s1 = 0.0;
                 for (int e = 0; e < GT_E; ++e) {
-                    const int r = chunk * 64 + (e >> 1) * 4 + ir;
+                    const int r = (chunk * (GT_E / 2) + (e >> 1)) * 4 + ir;
                     const int c = c0 + (e & 1);
                     double g0, g1;
                     factor_dlog_theta(f, xc[f.dim * TILE + c], xr[f.dim * TILE + r], g0, g1);
                     const double p = pw[e * 256 + tid];
-                    s0 += p * g0;
-                    s1 += p * g1;
+                    s0 = fma(p, g0, s0);
+                    s1 = fma(p, g1, s1);
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    s0 += __shfl_down_sync(0xffffffffu, s0, o);
-                    s1 += __shfl_down_sync(0xffffffffu, s1, o);
-                }
-                if (lane == 0) {
-                    acc[warp * GT_SLOTS + f.p0] += s0;
-                    if (f.p1 >= 0) acc[warp * GT_SLOTS + f.p1] += s1;
-                }
+                acc[f.p0 * 256 + tid] += s0;
+                if (f.p1 >= 0) acc[f.p1 * 256 + tid] += s1;
             }
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) trw += __shfl_down_sync(0xffffffffu, trw, o);
-    if (lane == 0) acc[warp * GT_SLOTS + nslot] += trw;
+    acc[nslot * 256 + tid] = trw;
     __syncthreads();
-    if (tid <= nslot) {
-        double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += acc[w * GT_SLOTS + tid];
-        partial[(int64_t)blockIdx.x * (nslot + 1) + tid] = s;
+    // fixed-order tree over the 256 threads of each slot (bit-repeatable)
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int q = 0; q <= nslot; ++q) acc[q * 256 + tid] += acc[q * 256 + tid + o];
+        __syncthreads();
     }
+    if (tid <= nslot) partial[(int64_t)blockIdx.x * (nslot + 1) + tid] = acc[tid * 256];
 }
 
 // Deterministic second stage: one CTA per slot, fixed summation order.
@@ -285,7 +282,7 @@ void launch_grad_trace(const DevProgram& prog, const double* Xt, const double* a
     int T = (int)(Npad / TILE);
     int ntiles = T * (T + 1) / 2;
     size_t smem = (size_t)2 * D * TILE * sizeof(double) + 16 + (size_t)2 * GT_E * 256 * sizeof(double) +
-                  (size_t)8 * GT_SLOTS * sizeof(double);
+                  (size_t)(prog.ntheta + 1) * 256 * sizeof(double);
     cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     grad_trace_kernel<<<ntiles, 256, smem, s>>>(prog, Xt, Npad, alpha, kinv, Npad, kdiag, N, D, partial);
     grad_reduce_kernel<<<prog.ntheta + 1, 256, 0, s>>>(partial, ntiles, prog.ntheta + 1, out);

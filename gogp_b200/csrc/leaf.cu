@@ -34,26 +34,20 @@ __global__ void __launch_bounds__(512, 1) potrf_leaf_kernel(double* __restrict__
 
     const int r = tid >> 2, h = tid & 3;
     const double* Sr = S + r * LP;
+    // adiag[i] is kept right-looking: after column j, adiag[i] = A[i][i] - sum_{k<=j} L[i][k]^2, so
+    // the pivot of column j is read, not summed (each row's h == 0 thread maintains its own entry)
     for (int j = 0; j <= TILE; ++j) {
-        // two independent accumulator chains per sum keep the FP64 pipe busy
-        double s0 = 0.0, s1 = 0.0, p0 = 0.0, p1 = 0.0;
+        double s0 = 0.0, s1 = 0.0;  // two independent accumulator chains
         if (r >= j) {
-            if (j < TILE) {
+            if (r > j && j < TILE) {
                 const double* Sj = S + j * LP;
                 int k = h;
 #pragma unroll 2
                 for (; k + 4 < j; k += 8) {
-                    const double l0 = Sj[k], l1 = Sj[k + 4];
-                    s0 = fma(Sr[k], l0, s0);
-                    s1 = fma(Sr[k + 4], l1, s1);
-                    p0 = fma(l0, l0, p0);
-                    p1 = fma(l1, l1, p1);
+                    s0 = fma(Sr[k], Sj[k], s0);
+                    s1 = fma(Sr[k + 4], Sj[k + 4], s1);
                 }
-                if (k < j) {
-                    const double l0 = Sj[k];
-                    s0 = fma(Sr[k], l0, s0);
-                    p0 = fma(l0, l0, p0);
-                }
+                if (k < j) s0 = fma(Sr[k], Sj[k], s0);
             }
         } else if (r < j - 1) {
             const double* Sj = S + (j - 1) * LP;
@@ -65,23 +59,24 @@ __global__ void __launch_bounds__(512, 1) potrf_leaf_kernel(double* __restrict__
             }
             if (k < j - 1) s0 = fma(Sj[k], Sr[k + 1], s0);
         }
-        double s = s0 + s1, p = p0 + p1;
+        double s = s0 + s1;
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        p += __shfl_xor_sync(0xffffffffu, p, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        p += __shfl_xor_sync(0xffffffffu, p, 2);
         if (h == 0) {
             if (r >= j) {
                 if (j < TILE) {
-                    double ajj = adiag[j] - p;
+                    double ajj = adiag[j];
                     if (!(ajj > 0.0)) {  // not positive definite (or NaN): flag, keep going
                         if (r == j) atomicCAS(info, 0, base + j + 1);
                         ajj = 1.0;
                     }
-                    if (r == j)
+                    if (r == j) {
                         S[j * LP + j] = sqrt(ajj);
-                    else
-                        S[r * LP + j] = (Sr[j] - s) * rsqrt(ajj);  // one reciprocal square root, no divide
+                    } else {
+                        const double l = (Sr[j] - s) * rsqrt(ajj);  // one reciprocal square root, no divide
+                        S[r * LP + j] = l;
+                        adiag[r] = fma(-l, l, adiag[r]);
+                    }
                 }
             } else {
                 const double dj = 1.0 / S[(j - 1) * LP + (j - 1)];
