@@ -15,6 +15,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <vector>
+
 namespace gogp {
 
 constexpr int64_t kTile = 128;
@@ -113,6 +115,51 @@ struct Blocked {
         // U12 = -U11 L21^T (U11 upper triangular: k >= row), then U12 <- U12 L22^-T
         be.gemm(at(Bm, o, o + n1), ld, at(Bm, o, o), ld, at(A, o + n1, o), ld, n1, n2, n1, -1.0, 0.0, BL_KTRI, nullptr);
         trsm(at(Bm, o, o + n1), ld, n1, o + n1, n2);
+    }
+
+    // The same inverse, traversed level by level instead of depth first: the diagonal blocks
+    // of size <= par_block are mutually independent (each a long chain of small, latency-bound
+    // launches), and so are the nodes of one recursion level, so the backend may spread them
+    // over concurrent streams (par_begin / par_use / par_end).  Same arithmetic as trtri_t.
+    struct Node {
+        int64_t o, n;
+    };
+    void collect(int64_t o, int64_t n, int depth, int64_t par_block, std::vector<Node>& leaves,
+                 std::vector<std::vector<Node>>& levels) {
+        if (n <= par_block || n == kTile) {
+            leaves.push_back({o, n});
+            return;
+        }
+        const int64_t n1 = split(n);
+        collect(o, n1, depth + 1, par_block, leaves, levels);
+        collect(o + n1, n - n1, depth + 1, par_block, leaves, levels);
+        if ((int)levels.size() <= depth) levels.resize(depth + 1);
+        levels[depth].push_back({o, n});
+    }
+    void trtri_t_levels(double* Bm, int64_t n, int64_t par_block) {
+        std::vector<Node> leaves;
+        std::vector<std::vector<Node>> levels;
+        collect(0, n, 0, par_block, leaves, levels);
+        be.par_begin();
+        for (size_t i = 0; i < leaves.size(); ++i) {
+            be.par_use((int)i);
+            trtri_t(Bm, leaves[i].o, leaves[i].n);
+        }
+        be.par_end();
+        for (int d = (int)levels.size() - 1; d >= 0; --d) {
+            const bool par = levels[d].size() > 1;
+            if (par) be.par_begin();
+            for (size_t i = 0; i < levels[d].size(); ++i) {
+                const int64_t o = levels[d][i].o, nn = levels[d][i].n, n1 = split(nn), n2 = nn - n1;
+                if (par) be.par_use((int)i);
+                be.set_scratch_row(o);
+                be.gemm(at(Bm, o, o + n1), ld, at(Bm, o, o), ld, at(A, o + n1, o), ld, n1, n2, n1, -1.0, 0.0, BL_KTRI,
+                        nullptr);
+                trsm(at(Bm, o, o + n1), ld, n1, o + n1, n2);
+            }
+            if (par) be.par_end();
+            be.set_scratch_row(0);
+        }
     }
 
     // K^-1 = U U^T: strictly-lower tiles into Bm's lower triangle, diagonal tiles into dg

@@ -21,6 +21,7 @@ namespace {
 constexpr double kNoNoise = 1e-5;  // gp/gp.go:43
 constexpr int64_t kProduceChunk = 8192;
 constexpr int64_t kOutOfPlaceRows = 2048;
+constexpr int kParStreams = 4;
 
 inline int64_t pad_tile(int64_t n) { return n <= 0 ? 0 : ((n + TILE - 1) / TILE) * TILE; }
 
@@ -31,6 +32,15 @@ inline int64_t rl_max() {
     if (v < 0) {
         const char* e = getenv("GOGP_RL_MAX");
         v = e ? atoll(e) : 4096;  // measured on B200 at N = 32768: potrf 431 ms (0) -> 412 ms (4096)
+    }
+    return v;
+}
+// Diagonal blocks up to this size are inverted concurrently on side streams (0: depth-first, one stream).
+inline int64_t par_block() {
+    static int64_t v = -1;
+    if (v < 0) {
+        const char* e = getenv("GOGP_PAR_BLOCK");
+        v = e ? atoll(e) : 1024;  // measured at N = 32768: potri 720.8 ms (0) -> 689.0 ms (1024)
     }
     return v;
 }
@@ -84,17 +94,42 @@ struct CudaBackend {
     GemmProfile* prof;
     double* scratch = nullptr;   // [scratch_rows][128]: out-of-place target of large in-place solves
     int64_t scratch_rows = 0;
+    // concurrency over independent sub-problems (Blocked::trtri_t_levels)
+    cudaStream_t* side = nullptr;  // kParStreams side streams
+    cudaEvent_t* side_ev = nullptr;
+    cudaEvent_t fork_ev = nullptr;
+    cudaStream_t main_stream = nullptr;
+    int64_t scratch_row = 0;
+    void par_begin() {
+        if (!side) return;
+        main_stream = s;
+        cudaEventRecord(fork_ev, main_stream);
+        for (int i = 0; i < kParStreams; ++i) cudaStreamWaitEvent(side[i], fork_ev, 0);
+    }
+    void par_use(int i) {
+        if (side) s = side[i % kParStreams];
+    }
+    void par_end() {
+        if (!side) return;
+        s = main_stream;
+        for (int i = 0; i < kParStreams; ++i) {
+            cudaEventRecord(side_ev[i], side[i]);
+            cudaStreamWaitEvent(main_stream, side_ev[i], 0);
+        }
+    }
+    void set_scratch_row(int64_t r) { scratch_row = r; }
     void gemm(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m, int64_t n,
               int64_t k, double alpha, double beta, int mode, double* cdiag) {
         const bool p = prof && prof->on;
         if (p) cudaEventRecord(prof->next(), s);
-        if ((mode & GEMM_INPLACE) && scratch && m >= kOutOfPlaceRows && m <= scratch_rows && n == TILE) {
+        if ((mode & GEMM_INPLACE) && scratch && m >= kOutOfPlaceRows && scratch_row + m <= scratch_rows && n == TILE) {
+            double* scr = scratch + scratch_row * TILE;  // concurrent nodes own disjoint row ranges
             // X = B Winv^T for many rows: the faster 2-CTA/SM shape cannot run in place (two CTAs
             // would share rows), so it writes to scratch and a copy brings the block back.  Its
             // 90 KB CTAs also interleave with a concurrent bulk GEMM, which the 160 KB in-place
             // shape cannot (it would wait for an entire SM to drain).
-            launch_dgemm_nt(scratch, TILE, A, lda, B, ldb, m, n, k, alpha, 0.0, GEMM_FULL, nullptr, s);
-            launch_copy_block(C, ldc, scratch, TILE, m, TILE, s);
+            launch_dgemm_nt(scr, TILE, A, lda, B, ldb, m, n, k, alpha, 0.0, GEMM_FULL, nullptr, s);
+            launch_copy_block(C, ldc, scr, TILE, m, TILE, s);
             ++*launches;
         } else {
             launch_dgemm_nt(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s);
@@ -145,10 +180,18 @@ struct gogp_handle {
     int64_t capM = 0, capBt = 0;
 
     bool has_data = false, factored = false, have_kinv = false, with_obs = false;
+    // evaluation memo: infer.FuncGrad evaluates Observe twice at the same
+    // point (value, then value + gradient); the second call is answered from the cached factor
+    bool memo_valid = false;
+    uint64_t memo_key = 0;
+    int64_t memo_hits = 0;
     double lml = 0.0;
     std::string err;
     double phase_ms[GOGP_NPHASE] = {0};
     cudaEvent_t ev[10] = {nullptr};
+    cudaStream_t side[kParStreams] = {nullptr};
+    cudaEvent_t side_ev[kParStreams] = {nullptr};
+    cudaEvent_t fork_ev = nullptr;
     int64_t launches = 0;
     GemmProfile prof;
 };
@@ -230,6 +273,17 @@ gogp_status ensure_grad_capacity(gogp_handle* h) {
     return GOGP_OK;
 }
 
+inline uint64_t hash_bytes(uint64_t h, const void* p, size_t n) {
+    // 64-bit multiply-xorshift over 8-byte words (inputs are float64 arrays)
+    const uint64_t* w = static_cast<const uint64_t*>(p);
+    for (size_t i = 0; i < n / 8; ++i) {
+        h ^= w[i];
+        h *= 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    return h;
+}
+
 // Upload X (N x D) and Y (N); build the dimension-major copy.
 gogp_status upload_data(gogp_handle* h, const double* X, const double* Y, int64_t N) {
     if (N < 0) return fail(h, GOGP_BAD_ARGUMENT, "negative N");
@@ -239,6 +293,7 @@ gogp_status upload_data(gogp_handle* h, const double* X, const double* Y, int64_
     h->has_data = true;
     h->factored = false;
     h->have_kinv = false;
+    h->memo_valid = false;
     if (N == 0) return GOGP_OK;
     if (!X || !Y) return fail(h, GOGP_BAD_ARGUMENT, "X and Y must be given when N > 0");
     gogp_status st = ensure_capacity(h, Npad);
@@ -265,7 +320,11 @@ gogp_status absorb(gogp_handle* h) {
     h->factored = false;
     h->have_kinv = false;
     for (double& m : h->phase_ms) m = 0.0;
-    if (!h->has_data) return fail(h, GOGP_NOT_READY, "no observations: call gogp_set_data or pass X, Y");
+    if (!h->has_data) {  // gp.X was never assigned: len(gp.X) == 0, the prior (gp/gp.go:101-104)
+        h->N = 0;
+        h->Npad = 0;
+        h->has_data = true;
+    }
     if (h->N == 0) {
         h->lml = 0.0;
         h->factored = true;
@@ -358,6 +417,9 @@ gogp_status gogp_create(int ndim, const gogp_op* simil, int n_simil_ops, int nth
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+    for (auto& st : h->side) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& ev : h->side_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     CK(cudaMalloc(&h->dRed, 64 * sizeof(double)));
     CK(cudaMalloc(&h->dInfo, sizeof(int)));
     set_theta(h, h->theta_s.data(), h->theta_n.data());
@@ -379,6 +441,11 @@ void gogp_destroy(gogp_handle* h) {
     for (auto& ev : h->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof.ev) cudaEventDestroy(ev);
+    for (auto& st : h->side)
+        if (st) cudaStreamDestroy(st);
+    for (auto& ev : h->side_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -400,8 +467,24 @@ gogp_status gogp_observe(gogp_handle* h, const double* log_theta, int with_obs, 
     std::vector<double> ts(h->nts > 0 ? h->nts : 1), tn(h->ntn > 0 ? h->ntn : 1);
     for (int i = 0; i < h->nts; ++i) ts[i] = std::exp(log_theta[i]);  // gp/gp.go:378-381
     for (int i = 0; i < h->ntn; ++i) tn[i] = std::exp(log_theta[h->nts + i]);
-    set_theta(h, ts.data(), tn.data());
     if (with_obs && N > 0 && (!X || !Y)) return fail(h, GOGP_BAD_ARGUMENT, "with_obs needs X and Y");
+    // memo: same parameters on the same observations as the last successful evaluation
+    uint64_t key = 0x243F6A8885A308D3ull ^ (uint64_t)(with_obs != 0) ^ ((uint64_t)(X != nullptr) << 1);
+    key = hash_bytes(key, log_theta, (size_t)(h->nts + h->ntn) * 8);
+    if (X) {
+        key = hash_bytes(key ^ (uint64_t)N, X, (size_t)N * h->ndim * 8);
+        key = hash_bytes(key, Y, (size_t)N * 8);
+    }
+    const bool same_data = X ? true : h->has_data;  // resident data: any gogp_set_data clears the memo
+    if (h->memo_valid && h->factored && same_data && key == h->memo_key && (with_obs != 0) == h->with_obs &&
+        (!X || N == h->N)) {
+        ++h->memo_hits;
+        for (double& m : h->phase_ms) m = 0.0;
+        *lml = h->lml;
+        return GOGP_OK;
+    }
+    h->memo_valid = false;
+    set_theta(h, ts.data(), tn.data());
     CK(cudaEventRecord(h->ev[4], h->stream));
     if (with_obs || X) {
         gogp_status st = upload_data(h, X, Y, N);
@@ -416,6 +499,8 @@ gogp_status gogp_observe(gogp_handle* h, const double* log_theta, int with_obs, 
         cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
         h->phase_ms[GOGP_PHASE_UPLOAD] = ms;
     }
+    h->memo_key = key;
+    h->memo_valid = true;
     *lml = h->lml;
     return GOGP_OK;
 }
@@ -464,7 +549,14 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
     if (!h->have_kinv) {
         CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
         Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
-        bl.trtri_t(h->dB, 0, Npad);
+        if (par_block() > 0) {
+            be.side = h->side;
+            be.side_ev = h->side_ev;
+            be.fork_ev = h->fork_ev;
+            bl.trtri_t_levels(h->dB, Npad, par_block());
+        } else {
+            bl.trtri_t(h->dB, 0, Npad);
+        }
         bl.lauum(h->dB, h->dDg, Npad);
         h->have_kinv = true;
     }
@@ -658,6 +750,38 @@ gogp_status gogp_debug_fp64_peak(gogp_handle* h, int which, double* tflops) {
     }
     CK(cudaGetLastError());
     *tflops = best;
+    return GOGP_OK;
+}
+
+gogp_status gogp_debug_leaf(gogp_handle* h, int variant, int iters, double* usec) {
+    if (!h || !usec || iters <= 0) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    double *A = nullptr, *W = nullptr;
+    const int64_t ld = 4096;
+    CK(cudaMalloc(&A, (size_t)TILE * ld * sizeof(double)));
+    CK(cudaMalloc(&W, (size_t)TILE * TILE * sizeof(double)));
+    set_leaf_variant(variant);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        float total = 0.f;
+        for (int i = 0; i < iters; ++i) {
+            launch_fill(A, TILE * ld, 0.01, h->stream);          // SPD tile: 0.01 everywhere ...
+            launch_fill_diag(A, ld + 1, TILE, 2.0, h->stream);   // ... and 2 on the diagonal
+            cudaEventRecord(h->ev[0], h->stream);
+            launch_potrf_leaf(A, ld, W, h->dInfo, 0, h->stream);
+            cudaEventRecord(h->ev[1], h->stream);
+            cudaStreamSynchronize(h->stream);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+            total += ms;
+        }
+        if (total < best) best = total;
+    }
+    set_leaf_variant(0);
+    cudaFree(A);
+    cudaFree(W);
+    CK(cudaGetLastError());
+    *usec = best / iters * 1e3;
     return GOGP_OK;
 }
 

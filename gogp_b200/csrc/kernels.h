@@ -65,6 +65,7 @@ double fp64_peak_flops_per_launch(int which, int variant, int iters, int nsm);
 // and its inverse into winv (128x128 row-major lower).  info: 0 or 1-based index
 // of the first non-positive pivot (global index = base + local).
 void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s);
+void set_leaf_variant(int v);  // timing aid, see leaf.cu
 // dst tile (ld) = winv^T (upper triangular, strictly-lower zeroed).
 void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t s);
 // Blocked triangular solves with the tile inverses.  fwd: out = L^-1 rhs; bwd: out = L^-T rhs.
@@ -78,6 +79,7 @@ void launch_copy_block(double* dst, int64_t ldd, const double* src, int64_t lds,
 void launch_axpy(double* y, const double* x, double a, int64_t n, cudaStream_t s);
 // v[i] = value for i in [0, n)
 void launch_fill(double* v, int64_t n, double value, cudaStream_t s);
+void launch_fill_diag(double* v, int64_t stride, int n, double value, cudaStream_t s);
 // pseudo-random fill in (-0.5, 0.5) for microbenchmarks
 void launch_fill_pattern(double* v, int64_t n, cudaStream_t s);
 // out[0] = sum_i log L_ii (i < N), out[1] = sum_i y_i alpha_i

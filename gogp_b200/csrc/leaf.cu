@@ -308,9 +308,18 @@ void launch_copy_block(double* dst, int64_t ldd, const double* src, int64_t lds,
 void launch_fill(double* v, int64_t n, double value, cudaStream_t s) {
     if (n > 0) fill_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(v, n, value, 0);
 }
+__global__ void fill_diag_kernel(double* v, int64_t stride, int n, double value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[(int64_t)i * stride] = value;
+}
+void launch_fill_diag(double* v, int64_t stride, int n, double value, cudaStream_t s) {
+    fill_diag_kernel<<<(n + 127) / 128, 128, 0, s>>>(v, stride, n, value);
+}
 void launch_fill_pattern(double* v, int64_t n, cudaStream_t s) {
     if (n > 0) fill_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(v, n, 0.0, 1);
 }
+
+void set_leaf_variant(int) {}  // kept for gogp_debug_leaf; the shipped kernel has one variant
 
 void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s) {
     const size_t smem = (size_t)TILE * LP * sizeof(double);

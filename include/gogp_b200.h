@@ -213,6 +213,10 @@ gogp_status gogp_debug_build(gogp_handle* h, const double* theta_simil, const do
  * (mma.sync m8n8k4 f64), 1 DFMA.  Returns TFLOP/s in *tflops. */
 gogp_status gogp_debug_fp64_peak(gogp_handle* h, int which, double* tflops);
 
+/* Device time of the 128 x 128 tile Cholesky+inverse kernel in microseconds (variant 0; other
+ * variants leave parts out and exist to attribute its time). */
+gogp_status gogp_debug_leaf(gogp_handle* h, int variant, int iters, double* usec);
+
 /* One C -= A B^T of size n (tiles of the trailing update), timed; returns
  * TFLOP/s.  mode 0 full, 1 lower-triangular (SYRK). */
 gogp_status gogp_debug_gemm(gogp_handle* h, int64_t n, int64_t k, int mode, int iters, double* tflops);

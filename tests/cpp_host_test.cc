@@ -1,0 +1,74 @@
+// C++ host mirror (include/gogp_b200.hpp) against the reference's TestElementalModel and
+// TestProduce tables (gp/gp_test.go:23-120, 180-229).  "nodevice" mode: expect the loud
+// failure the product path must give without a GPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "../include/gogp_b200.hpp"
+
+using namespace gogp;
+
+static int fails = 0;
+#define CHECK(c)                                                 \
+    do {                                                         \
+        if (!(c)) {                                              \
+            std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); \
+            ++fails;                                             \
+        }                                                        \
+    } while (0)
+
+int main(int argc, char** argv) {
+    if (argc > 1 && !std::strcmp(argv[1], "nodevice")) {
+        GP g(1, Normal, ConstantNoise(0.1));
+        std::vector<double> x{0.0};
+        try {
+            g.Observe(x);
+        } catch (const Panic& p) {
+            std::printf("panic: %s\n", p.what());
+            return p.status == GOGP_CUDA_ERROR ? 0 : 2;
+        }
+        return 1;
+    }
+    struct E { const char* name; bool uniform; double noise; std::vector<double> x; double ll; };
+    std::vector<E> cases = {
+        {"prior", false, 0.0, {0}, 0.0},
+        {"single", false, 0.0, {0, 0, 1}, -1.418939},
+        {"nonoise", false, 0.0, {0, 0, 1, 1, 0}, -2.399528},
+        {"withnoise", false, 0.1, {1, -2, -1, 1, 0}, -4.321055},
+        {"uninoise", true, 0.0, {1, 1, -1, -1, 1, 0}, -4.018110},
+    };
+    for (auto& c : cases) {
+        GP g(1, Normal, c.uniform ? UniformNoise() : ConstantNoise(c.noise));
+        std::vector<double> x = c.x;
+        const double ll = g.Observe(x);
+        std::vector<double> dll = g.Gradient();
+        CHECK(std::fabs(ll - c.ll) < 1e-6);
+        CHECK(dll.size() == c.x.size());
+        for (size_t j = 0; j < x.size(); ++j) {  // forward difference, gp/gp_test.go:242-252
+            std::vector<double> xj = c.x;
+            xj[j] += 1e-8;
+            const double llj = g.Observe(xj);
+            CHECK(std::fabs(dll[j] - (llj - ll) / 1e-8) <= 1e-4);
+        }
+        for (size_t j = 0; j < x.size(); ++j) CHECK(std::fabs(x[j] - c.x[j]) < 1e-15);  // exp/log round trip
+        std::printf("%s ll=%.6f ok\n", c.name, ll);
+    }
+    {  // TestProduce "noise", gp/gp_test.go:108-120
+        GP g(1, Normal, ConstantNoise(0.1));
+        g.ThetaSimil = {1.0};
+        Error e = g.Absorb({{0}, {1}}, {1, -1});
+        CHECK(e.ok());
+        std::vector<double> mu, sigma;
+        e = g.Produce({{-2.}, {3.}}, mu, sigma);
+        CHECK(e.ok());
+        CHECK(std::fabs(mu[0] - 0.307895) < 1e-6 && std::fabs(mu[1] + 0.307895) < 1e-6);
+        CHECK(std::fabs(sigma[0] - 0.987037) < 1e-6 && std::fabs(sigma[1] - 0.987037) < 1e-6);
+        GP bad(1, Normal, ConstantNoise(0.0));
+        bad.ThetaSimil = {1.0};
+        e = bad.Absorb({{0}, {0}}, {1, 2});  // singular K: an error, not a panic, from Absorb
+        CHECK(!e.ok() && e.status == GOGP_NOT_POSITIVE_DEFINITE);
+    }
+    std::printf(fails ? "FAILED %d\n" : "all ok\n", fails);
+    return fails ? 1 : 0;
+}

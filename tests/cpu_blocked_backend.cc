@@ -81,6 +81,10 @@ struct HostBackend {
                 winv[i * n + c] = s / A[i * ld + i];
             }
     }
+    void par_begin() {}
+    void par_use(int) {}
+    void par_end() {}
+    void set_scratch_row(int64_t) {}
     void trtri_leaf(const double* winv, double* dst, int64_t ld) {
         const int n = (int)kTile;
         for (int r = 0; r < n; ++r)
@@ -109,7 +113,10 @@ int cpu_blocked_potrf(double* A, int64_t n, double* winv) {
 void cpu_blocked_kinv(double* L, int64_t n, double* winv, double* Bm, double* dg) {
     HostBackend be;
     Blocked<HostBackend> bl{be, L, n, winv, g_rl_max, g_rl_max};
-    bl.trtri_t(Bm, 0, n);
+    if (g_rl_max == 1024)
+        bl.trtri_t_levels(Bm, n, 256);  // level-order traversal, small parallel blocks
+    else
+        bl.trtri_t(Bm, 0, n);
     bl.lauum(Bm, dg, n);
 }
 

@@ -267,3 +267,30 @@ def test_repeatable_and_handle_reuse():
         res.append((dg.Observe(logt.copy()), dg.Gradient()))
     assert res[0][0] == res[3][0]
     assert np.array_equal(res[0][1], res[3][1])
+
+
+def test_evaluation_memo_for_funcgrad_pattern():
+    """infer.FuncGrad evaluates Observe(x) for the value and again for the gradient
+    (SURVEY.md section 3.4): the repeat at the same point costs no kernel launch."""
+    name, N = "hyperpriors", 400
+    X, y, logt = cases.synth(name, N, seed=8)
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    v1 = dg.Observe(logt.copy())
+    n1 = dg.Launches()
+    v2 = dg.Observe(logt.copy())          # Func(x) then Grad(x): same x
+    assert v2 == v1 and dg.Launches() == n1
+    g = dg.Gradient()
+    ref = og.observe(logt.copy())
+    assert abs(v1 - ref) <= LML_TOL * max(abs(ref), N)
+    assert _grad_err(g, og.gradient()) <= GRAD_TOL
+    y2 = y.copy()
+    y2[0] += 1e-3                          # same theta, different data: must recompute
+    dg.Y = y2
+    v3 = dg.Observe(logt.copy())
+    assert dg.Launches() > n1 and v3 != v1
+    og.Y = y2
+    ref3 = og.observe(logt.copy())
+    assert abs(v3 - ref3) <= LML_TOL * max(abs(ref3), N)
