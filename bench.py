@@ -27,6 +27,11 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1; the CPU legs (reference arm, cpu_baseline) must be free to use
+# every host core, so lift the cap before NumPy/OpenBLAS load (rank 0 is the only rank that runs them)
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -113,6 +118,16 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def blas_threads():
+    """Threads the BLAS behind NumPy will actually use (all host cores unless capped)."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count()
+
+
 def cpu_port_eval(N_s, mode, truth):
     """One Observe+Gradient of the oracle port on the host (TEST INFRASTRUCTURE used as the
     timed CPU baseline, never as the product path)."""
@@ -143,6 +158,7 @@ def run_reference(args, rank):
     N = args.n
     N_s = min(N, args.cpu_sample_n)
     _, _, truth = synth(8, 0)
+    blas_threads()
     for _ in range(args.warmup):
         if N_s > 1024:
             break  # a warm-up step costs as much as a timed one; BLAS threads need no warming
@@ -152,7 +168,7 @@ def run_reference(args, rank):
     t_full = float(np.mean([extrapolate(*r, N_s, N) for r in runs]))
     scale = t_full / t
     value = 1.0 / t_full
-    cores = os.cpu_count()
+    cores = blas_threads()
     sample = ("oracle port of gp/gp.go in literal mode (materialised dK, per-parameter GEMM + Cholesky solve + trace) "
               "on NumPy/OpenBLAS -- not gonum, not Go; timed at N=%d (%.2f s/evaluation), EXTRAPOLATED to N=%d: "
               "element work x (N/N_s)^2, dense algebra x (N/N_s)^3 (the literal algorithm needs (P+5) N^2 8 B = "
@@ -342,11 +358,12 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             N_s = min(N, args.cpu_sample_n)
+            ncores = blas_threads()
             lit = cpu_port_eval(N_s, "literal", truth)
             N_f = min(N, 2 * args.cpu_sample_n)
             fast = cpu_port_eval(N_f, "fast", truth)
             out["cpu_baseline"] = {
-                "value": 1.0 / extrapolate(*lit, N_s, N), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "value": 1.0 / extrapolate(*lit, N_s, N), "unit": UNIT, "cores": ncores, "kind": "port",
                 "sample": "oracle port of gp/gp.go, literal mode (per-parameter GEMM + Cholesky solve + trace), "
                           "NumPy/OpenBLAS, one evaluation at N=%d took %.2f s (%.2f s element work, %.2f s dense "
                           "algebra); EXTRAPOLATED to N=%d: element work x (N/N_s)^2, dense algebra x (N/N_s)^3"
