@@ -549,7 +549,8 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
     if (!h->have_kinv) {
         CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
         Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
-        if (par_block() > 0) {
+        // per-launch accounting needs launches that do not overlap: profile on one stream
+        if (par_block() > 0 && !h->prof.on) {
             be.side = h->side;
             be.side_ev = h->side_ev;
             be.fork_ev = h->fork_ev;

@@ -294,3 +294,52 @@ def test_evaluation_memo_for_funcgrad_pattern():
     og.Y = y2
     ref3 = og.observe(logt.copy())
     assert abs(v3 - ref3) <= LML_TOL * max(abs(ref3), N)
+
+
+def test_full_size_properties_n32768():
+    """BASELINE size (N = 32768, the bench workload): the oracle cannot run here in test time, so
+    size-independent properties instead -- (i) the gradient agrees with a central difference of the
+    LML along a random direction, (ii) two different factorisation paths of the library (recursive
+    single-GPU, block-cyclic with 2048-blocks) give the same LML, (iii) repeat evaluation is
+    bit-identical, (iv) predictions at training inputs reproduce y within the noise level."""
+    import bench
+    from gogp_b200 import GP, kernel as k
+    from gogp_b200.dist_chol import BlockCyclicCholesky, CudaBlocks
+    N, D = 32768, 8
+    e = k.Param(0)
+    for d in range(D):
+        e = e * k.Normal.Of(l=1 + d, dim=d)
+    e = e * k.Periodic.Of(l=1 + D, p=2 + D, dim=0)
+    X, y, truth = bench.synth(N, 0)
+    g = GP(NDim=D, Simil=e, Noise=k.UniformNoise)
+    g.X, g.Y = X, y
+    t0 = bench.theta_for(truth, 0, 0)
+    lml = g.Observe(t0.copy())
+    grad = g.Gradient()
+    assert np.all(np.isfinite(grad)) and np.isfinite(lml)
+    # (iv) before theta changes: posterior mean at 64 training points
+    mu, sigma, err = g.Produce(X[:64])
+    assert err is None
+    assert np.max(np.abs(mu - y[:64])) < 0.5 and np.all(sigma < 0.2)
+    # (i) directional derivative, central difference with h = 1e-4 (truncation ~1e-8 relative)
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(len(t0))
+    v /= np.linalg.norm(v)
+    h = 1e-4
+    fd = (g.Observe(t0 + h * v) - g.Observe(t0 - h * v)) / (2 * h)
+    assert abs(fd - grad @ v) <= 1e-5 * max(1.0, abs(grad @ v)), (fd, grad @ v)
+    # (iii) bit-repeatability
+    lml2 = g.Observe(t0.copy() + 0.0)
+    g2 = g.Gradient()
+    assert lml2 == lml and np.array_equal(g2, grad)
+    g.close()
+    # (ii) the block-cyclic path on the same inputs
+    be = CudaBlocks(e, k.UniformNoise, D, 0)
+    be.set_inputs(X, 2048)
+    ch = BlockCyclicCholesky(be, N, 2048)
+    th = np.exp(t0)
+    ch.build(th[:D + 3], th[D + 3:])
+    ch.factor()
+    lml_bc = ch.solve_lml(y)
+    be.close()
+    assert abs(lml_bc - lml) <= 1e-11 * max(abs(lml), N), (lml_bc, lml)
