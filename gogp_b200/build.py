@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libgogp_b200.so")
 
-CU_SOURCES = ["capi.cu", "cov.cu", "dgemm.cu", "leaf.cu"]
+CU_SOURCES = ["capi.cu", "cov.cu", "dgemm.cu", "dgemm_tma.cu", "leaf.cu"]
 CC_SOURCES = ["program.cc"]
 HEADERS = ["program.h", "kexpr.cuh", "kernels.h", "blocked.hpp", os.path.join("..", "..", "include", "gogp_b200.h")]
 

@@ -231,16 +231,23 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* sink)
 
 }  // namespace
 
-static int g_gemm_cfg = -1;  // 0: 128x128 1 CTA/SM, 1: 128x64 2 CTAs/SM (env GOGP_GEMM_CFG, default 1)
+static int g_gemm_cfg = -1;  // 0: 128x128 1 CTA/SM, 1: 128x64 2 CTAs/SM, 2: TMA + mbarrier warp-specialised
+                             // (env GOGP_GEMM_CFG, default 1)
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
 void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s) {
+    static int64_t tma_min_k = 0;
     if (g_gemm_cfg < 0) {
         const char* e = getenv("GOGP_GEMM_CFG");
-        g_gemm_cfg = e ? atoi(e) : 1;
+        g_gemm_cfg = e ? atoi(e) : 2;
+        const char* mk = getenv("GOGP_TMA_MIN_K");
+        tma_min_k = mk ? atoll(mk) : 512;  // below it the 2-CTA cp.async shape has the lower per-tile latency
     }
     if (k <= 0) return;
+    if (g_gemm_cfg == 2 && k >= tma_min_k &&
+        launch_dgemm_tma(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s))
+        return;
     GemmArgs g;
     g.C = C;
     g.A = A;
@@ -255,7 +262,7 @@ void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const
     g.alpha = alpha;
     g.beta = beta;
     // C aliasing A needs a CTA that owns entire rows of the (128-wide) block
-    if (g_gemm_cfg == 0 || (mode & GEMM_INPLACE))
+    if (g_gemm_cfg == 0 || (mode & GEMM_INPLACE))  // (cfg 2 falls back to the 2-CTA shape below)
         launch_cfg<2, 4, 4, 1>(g, m, n, s);
     else
         launch_cfg<2, 2, 3, 2>(g, m, n, s);

@@ -54,6 +54,9 @@ enum GemmMode : int {
 // C[i][j] = beta*C[i][j] + alpha * sum_k A[i][k] B[j][k]; all of m, n, k multiples of 128.
 void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s);
+// TMA + mbarrier warp-specialised variant (dgemm_tma.cu); false: not available, use launch_dgemm_nt's kernels
+bool launch_dgemm_tma(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
+                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s);
 void set_gemm_config(int cfg);  // 0: 128x128 tiles, 1 CTA/SM; 1: 128x64 tiles, 2 CTAs/SM
 // register-only issue-rate microbenchmarks: which = 0 DMMA m8n8k4, 1 DFMA
 int fp64_peak_variants();
