@@ -43,12 +43,12 @@ WORKLOAD = "configs[2]: synthetic 8-D scaled Normal x Periodic + noise, N=32768,
 N_FULL, NDIM = 32768, 8
 NOMINAL_FP64_TFLOPS = 148 * 128 * 1.965e9 / 1e12  # 64 FP64 FMA/clk/SM at clocks.max.sm
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` capture profiles/r1_gemm_v2_ncu_raw.csv (a number taken under the profiler is evidence
+# `ncu --set full` capture profiles/r1_gemm_v3_tma_ncu_raw.csv (a number taken under the profiler is evidence
 # of traffic, never a timing): the 8192 x 8192 x 8192 C -= A B^T launch of tools/gemm_bench.py
-GEMM_NCU_TRAFFIC = {"dram_bytes": 6.285404e9 + 0.529176e9, "launch": "dgemm_nt_kernel<2,2,3,2>, m=n=k=8192",
-                    "algorithmic_bytes": 4 * 8192 * 8192 * 8, "duration_ms_under_ncu": 31.53,
-                    "dmma_pipe_pct_of_active": 94.86, "l2_hit_pct": 89.2,
-                    "source": "profiles/r1_gemm_v2_ncu_raw.csv"}
+GEMM_NCU_TRAFFIC = {"dram_bytes": 6.328994e9 + 0.530380e9, "launch": "dgemm_tma_kernel, m=n=k=8192",
+                    "algorithmic_bytes": 4 * 8192 * 8192 * 8, "duration_ms_under_ncu": 30.58,
+                    "dmma_pipe_pct_of_active": 97.87, "tensor_pipe_pct_of_elapsed": 94.26, "l2_hit_pct": 83.4,
+                    "source": "profiles/r1_gemm_v3_tma_ncu_raw.csv"}
 
 
 def synth(N, seed=0):
@@ -343,7 +343,7 @@ def main():
             "cholesky_tflops": float(N) ** 3 / 3 / (phases[2] * 1e-3) / 1e12 if phases[2] > 0 else None,
             "potri_tflops": 2 * float(N) ** 3 / 3 / (phases[4] * 1e-3) / 1e12 if phases[4] > 0 else None,
             "roofline": {
-                "bound": "tensor", "kernel": "dgemm_nt_kernel (DMMA.8x8x4)", "achieved": achieved, "peak": peak,
+                "bound": "tensor", "kernel": "dgemm_tma_kernel / dgemm_nt_kernel (DMMA.8x8x4)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": GEMM_NCU_TRAFFIC["dram_bytes"],
                 "traffic_note": GEMM_NCU_TRAFFIC,
                 "peak_source": "measured in this run: mma.sync.m8n8k4.f64 register-only issue-rate microbenchmark "
