@@ -206,19 +206,23 @@ class BlockCyclicCholesky:
             panel, pc_buf = self.panels[k % 2], self.pc_bufs[k % 2]
             self._bcast(self.lkk, ok)
             self._bcast(self.wkk, ok)
-            # panel solve on the ranks of process column k mod Pc, then whole-panel broadcast
+            # panel solve on the ranks of process column k mod Pc -- every source rank solves its own
+            # rows FIRST, so the Pr solves run concurrently -- then the whole panel is broadcast
             kc = k % self.Pc
+            srcs = []
             for rr in range(self.Pr):
                 rows = [I for I in self.rows_of[rr] if I > k]
                 if not rows:
                     continue
                 src = rr * self.Pc + kc
                 buf = panel[rr][:len(rows)]
+                srcs.append((src, buf))
                 if self.rank == src:
                     i0, j = self.ri[rows[0]], self.ci[k]
                     sub = self.local[i0 * NB:(i0 + len(rows)) * NB, j * NB:(j + 1) * NB]
                     be.trsm(sub, self.lkk, self.wkk)
                     buf.copy_(sub.reshape(len(rows), NB, NB))
+            for src, buf in srcs:
                 self._bcast(buf, src)
             # rows of the panel that face my block columns, in increasing J
             cols = [J for J in self.my_cols if J > k]
