@@ -123,6 +123,20 @@ func (gp *GP) handle() (*C.gogp_handle, error) {
 	return h, nil
 }
 
+// SetEvents hands the event table of tutorial/events' Simil{Events} (rows of from, to, discount)
+// to the device; used by kernel.Events leaves.
+func (gp *GP) SetEvents(events [][]float64) error {
+	h, err := gp.handle()
+	if err != nil {
+		return err
+	}
+	flat := flatten(events, 3)
+	if st := C.gogp_set_events(h, dptr(flat), C.int(len(events))); st != C.GOGP_OK {
+		return gp.fail(st)
+	}
+	return nil
+}
+
 // Close releases the device handle.
 func (gp *GP) Close() {
 	if gp.h != nil {

@@ -26,6 +26,7 @@ const (
 	opMatern32
 	opMatern52
 	opMatern52Textbook
+	opEvents
 )
 
 // Expr is a kernel given by its postfix descriptor.
@@ -84,6 +85,10 @@ func On(k Expr, dim, l int, lscale float64, p int, pscale float64) Expr {
 func Param(i int, scale float64) Expr {
 	return Expr{[]gp.Op{{Kind: opParam, Param: [2]int16{int16(i), 0}, Scale: [2]float64{scale, 1}}}, i + 1}
 }
+
+// Events is the discount factor of tutorial/events/kernel/kernel.go:33-44 on input coordinate
+// dim; the event table itself is handed to the device with gp.GP.SetEvents (gogp_set_events).
+func Events(dim int) Expr { return Expr{[]gp.Op{{Kind: opEvents, Dim: uint8(dim)}}, 0} }
 
 func Const(c float64) Expr { return Expr{[]gp.Op{{Kind: opConst, Constant: c}}, 0} }
 

@@ -16,13 +16,14 @@ OK, BAD_ARGUMENT, NOT_POSITIVE_DEFINITE, ILL_CONDITIONED, CUDA_ERROR, NCCL_ERROR
     UNSUPPORTED = range(9)
 
 # gogp_op_kind
-OP_CONST, OP_PARAM, OP_ADD, OP_MUL, OP_NORMAL, OP_PERIODIC, OP_MATERN32, OP_MATERN52, OP_MATERN52_TEXTBOOK = range(9)
+OP_CONST, OP_PARAM, OP_ADD, OP_MUL, OP_NORMAL, OP_PERIODIC, OP_MATERN32, OP_MATERN52, OP_MATERN52_TEXTBOOK, \
+    OP_EVENTS = range(10)
 
 PHASES = ("upload", "build", "potrf", "solve", "potri", "trace", "predict")
 
 # every symbol include/gogp_b200.h declares
 SYMBOLS = (
-    "gogp_create", "gogp_destroy", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_lml",
+    "gogp_create", "gogp_destroy", "gogp_set_events", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_lml",
     "gogp_produce", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
     "gogp_debug_gemm", "gogp_debug_leaf", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
@@ -60,6 +61,8 @@ def lib():
     L.gogp_create.restype = C.c_int
     L.gogp_destroy.argtypes = [H]
     L.gogp_destroy.restype = None
+    L.gogp_set_events.argtypes = [H, dp, C.c_int]
+    L.gogp_set_events.restype = C.c_int
     L.gogp_set_data.argtypes = [H, dp, dp, C.c_int64]
     L.gogp_set_data.restype = C.c_int
     L.gogp_observe.argtypes = [H, dp, C.c_int, dp, dp, C.c_int64, dp]

@@ -450,6 +450,16 @@ void gogp_destroy(gogp_handle* h) {
     delete h;
 }
 
+gogp_status gogp_set_events(gogp_handle* h, const double* events, int n) {
+    if (!h || n < 0 || (n > 0 && !events)) return GOGP_BAD_ARGUMENT;
+    if (n > kMaxEvents) return fail(h, GOGP_UNSUPPORTED, "at most 16 events");
+    h->simil.events.assign(events, events + 3 * n);
+    h->factored = false;
+    h->have_kinv = false;
+    h->memo_valid = false;
+    return GOGP_OK;
+}
+
 gogp_status gogp_set_data(gogp_handle* h, const double* X, const double* Y, int64_t N) {
     if (!h) return GOGP_BAD_ARGUMENT;
     CK(cudaSetDevice(h->dev));

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
             // phase 2: per-factor log-derivatives
             for (int fi = fb; fi < fe; ++fi) {
                 const DevFactor& f = prog.f[fi];
+                if (f.p0 < 0) continue;  // parameter-free factor (events)
                 double s0 = 0.0, s1 = 0.0;
                 for (int e = 0; e < GT_E; ++e) {
                     const int r = (chunk * (GT_E / 2) + (e >> 1)) * 4 + ir;

@@ -16,6 +16,17 @@ namespace gogp {
 
 // Length-scale divisions use the host-computed reciprocal i0 = 1/(scale*theta)
 // (d differs from the reference's r/l by at most one ulp).
+// tutorial/events/kernel/kernel.go:33-44: order the pair, the first event whose from- or to-boundary
+// lies in (lo, hi] discounts the similarity.
+__device__ __forceinline__ double events_value(const DevProgram& prog, double xa, double xb) {
+    const double lo = xa > xb ? xb : xa, hi = xa > xb ? xa : xb;
+    for (int e = 0; e < prog.nevents; ++e) {
+        const double from = prog.ev[e][0], to = prog.ev[e][1];
+        if ((lo < from && from <= hi) || (lo < to && to <= hi)) return prog.ev[e][2];
+    }
+    return 1.0;
+}
+
 __device__ __forceinline__ double factor_value(const DevFactor& f, double xa, double xb) {
     switch (f.kind) {
         case F_PARAM:
@@ -58,7 +69,7 @@ __device__ __forceinline__ double term_value(const DevProgram& prog, int t, XA x
     }
     for (; fi < fe; ++fi) {
         const DevFactor& f = prog.f[fi];
-        p *= factor_value(f, xa(f.dim), xb(f.dim));
+        p *= (f.kind == F_EVENTS) ? events_value(prog, xa(f.dim), xb(f.dim)) : factor_value(f, xa(f.dim), xb(f.dim));
     }
     return p;
 }
@@ -67,6 +78,9 @@ __device__ __forceinline__ double term_value(const DevProgram& prog, int t, XA x
 __device__ __forceinline__ void factor_dlog_theta(const DevFactor& f, double xa, double xb, double& g0, double& g1) {
     g1 = 0.0;
     switch (f.kind) {
+        case F_EVENTS:
+            g0 = 0.0;
+            return;
         case F_PARAM:
             g0 = 1.0;
             return;
@@ -103,6 +117,7 @@ __device__ __forceinline__ double factor_dlog_xa(const DevFactor& f, double xa, 
     double sg = (r > 0) - (r < 0);
     switch (f.kind) {
         case F_PARAM:
+        case F_EVENTS:  // piecewise constant in the inputs
             return 0.0;
         case F_NORMAL: {
             double d = r * f.i0;

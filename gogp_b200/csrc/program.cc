@@ -63,6 +63,14 @@ bool Program::lower(const gogp_op* ops, int n, int ntheta_, int ndim, bool allow
                 has_leaf = true;
                 break;
             }
+            case GOGP_OP_EVENTS: {
+                if (!allow_leaves) return bad("similarity leaf in a noise program", i);
+                if (op.dim >= ndim) return bad("input dimension out of range", i);
+                HostTerm t{1.0, {HostFactor{F_EVENTS, op.dim, -1, -1, 1.0, 1.0, 0.0}}};
+                stack.push_back({t});
+                has_leaf = true;
+                break;
+            }
             case GOGP_OP_ADD:
             case GOGP_OP_MUL: {
                 if (stack.size() < 2) return bad("stack underflow", i);
@@ -129,13 +137,16 @@ void Program::bind(const double* theta, DevProgram* out) const {
             d.dim = f.dim;
             d.p0 = f.p0;
             d.p1 = f.p1;
-            d.a0 = f.s0 * theta[f.p0];
+            d.a0 = f.p0 >= 0 ? f.s0 * theta[f.p0] : 1.0;
             d.a1 = f.p1 >= 0 ? f.s1 * theta[f.p1] : 0.0;
             d.i0 = 1.0 / d.a0;
             d.c = f.c;
         }
     }
     out->fbeg[out->nterms] = k;
+    out->nevents = (int)(events.size() / 3);
+    for (int e = 0; e < out->nevents; ++e)
+        for (int c = 0; c < 3; ++c) out->ev[e][c] = events[3 * e + c];
 }
 
 double Program::eval_scalar(const double* theta, double* dlog) const {

@@ -27,7 +27,9 @@ enum FactorKind : int {
     F_PERIODIC = 2,
     F_MATERN32 = 3,
     F_MATERN52 = 4,  // c = 1 (shipped) or 5/3 (textbook), in `c`
+    F_EVENTS = 5,    // parameter-free discount of the first event boundary between the two points
 };
+constexpr int kMaxEvents = 16;
 
 struct DevFactor {
     int kind;
@@ -45,6 +47,8 @@ struct DevProgram {
     int nnorm[kMaxTerms];  // leading Normal factors of each term (they share one exp)
     double coef[kMaxTerms];
     DevFactor f[kMaxFactors];
+    int nevents;
+    double ev[kMaxEvents][3];  // from, to, discount
 };
 
 struct HostFactor {
@@ -60,6 +64,7 @@ struct Program {
     int ntheta = 0;
     std::vector<HostTerm> terms;
     bool has_leaf = false;
+    std::vector<double> events;  // n x 3
 
     // Postfix -> sum of products.  Returns false and sets err when malformed or
     // too large.

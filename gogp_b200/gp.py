@@ -84,6 +84,12 @@ class GP:
                 L.gogp_destroy(h)
             raise GoGPPanic(st, msg)
         self._h, self._key = h, key
+        ev = getattr(self.Simil, "events", None)
+        if ev:
+            flat = np.ascontiguousarray(np.asarray(ev, dtype=np.float64).reshape(-1))
+            st = L.gogp_set_events(h, _lib.dptr(flat), len(ev))
+            if st != _lib.OK:
+                raise GoGPPanic(st, self._err(st))
         return h
 
     def close(self):

@@ -27,13 +27,14 @@ def _pidx(p):
 class Kernel:
     """An expression in postfix form + the number of parameters it declares."""
 
-    def __init__(self, ops, ntheta=None, is_noise=False):
+    def __init__(self, ops, ntheta=None, is_noise=False, events=None):
         self.ops = list(ops)
+        self.events = events  # the Events table of tutorial/events' Simil, if the expression has an Events leaf
         used = -1
         for o in self.ops:
             if o[0] == _lib.OP_PARAM:
                 used = max(used, o[2])
-            elif o[0] >= _lib.OP_NORMAL:
+            elif _lib.OP_NORMAL <= o[0] <= _lib.OP_MATERN52_TEXTBOOK:
                 used = max(used, o[2], o[3] if o[0] == _lib.OP_PERIODIC else -1)
         self._ntheta = used + 1 if ntheta is None else int(ntheta)
         if self._ntheta < used + 1:
@@ -47,7 +48,7 @@ class Kernel:
     def WithNTheta(self, n):
         """Declare more parameters than the expression uses (tutorial/anynoise's
         noise allocates one unused parameter, kernel.go:31-35)."""
-        return Kernel(self.ops, n, self.is_noise)
+        return Kernel(self.ops, n, self.is_noise, self.events)
 
     def Descriptor(self):
         """-> ctypes array of gogp_op"""
@@ -68,14 +69,14 @@ class Kernel:
     def __add__(self, o):
         o = Kernel._lift(o)
         return Kernel(self.ops + o.ops + [(_lib.OP_ADD, 0, 0, 0, 1.0, 1.0, 0.0)],
-                      max(self._ntheta, o._ntheta), self.is_noise and o.is_noise)
+                      max(self._ntheta, o._ntheta), self.is_noise and o.is_noise, self.events or o.events)
 
     __radd__ = __add__
 
     def __mul__(self, o):
         o = Kernel._lift(o)
         return Kernel(self.ops + o.ops + [(_lib.OP_MUL, 0, 0, 0, 1.0, 1.0, 0.0)],
-                      max(self._ntheta, o._ntheta), self.is_noise and o.is_noise)
+                      max(self._ntheta, o._ntheta), self.is_noise and o.is_noise, self.events or o.events)
 
     __rmul__ = __mul__
 
@@ -113,6 +114,15 @@ Periodic = _Stock(_lib.OP_PERIODIC, 2)                # kernel/kernel.go:34-47
 Matern32 = _Stock(_lib.OP_MATERN32, 1)                # kernel/kernel.go:60-73
 Matern52 = _Stock(_lib.OP_MATERN52, 1)                # kernel/kernel.go:79-92 (5/3 == 1 as shipped)
 Matern52Textbook = _Stock(_lib.OP_MATERN52_TEXTBOOK, 1)
+
+
+def Events(events, dim=0):
+    """The discount of tutorial/events/kernel/kernel.go:33-44 as a factor: 1, or the discount of
+    the first event (from, to, discount) whose from- or to-boundary separates the two points."""
+    ev = [tuple(float(v) for v in e) for e in events]
+    if any(len(e) != 3 for e in ev):
+        raise ValueError("an event is (from, to, discount)")
+    return Kernel([(_lib.OP_EVENTS, int(dim), 0, 0, 1.0, 1.0, 0.0)], 0, False, ev)
 
 
 def ConstantNoise(std):

@@ -62,7 +62,9 @@ typedef enum {
     GOGP_OP_PERIODIC = 5,        /* kernel.Periodic.Cov(l, p, xa, xb)  kernel/kernel.go:44-47 */
     GOGP_OP_MATERN32 = 6,        /* kernel.Matern32.Cov(l, xa, xb)     kernel/kernel.go:70-73 */
     GOGP_OP_MATERN52 = 7,        /* kernel.Matern52.Cov as shipped: 5/3 == 1, kernel/kernel.go:89-92 */
-    GOGP_OP_MATERN52_TEXTBOOK = 8 /* (1 + sqrt5 d + 5/3 d^2) exp(-sqrt5 d); not in the reference */
+    GOGP_OP_MATERN52_TEXTBOOK = 8, /* (1 + sqrt5 d + 5/3 d^2) exp(-sqrt5 d); not in the reference */
+    GOGP_OP_EVENTS = 9           /* tutorial/events/kernel/kernel.go:33-44: push the discount of the first event
+                                    (gogp_set_events) whose from- or to-boundary separates xa and xb on `dim`, else 1 */
 } gogp_op_kind;
 
 typedef struct {
@@ -100,6 +102,10 @@ gogp_status gogp_create(int ndim,
                         const gogp_op* noise, int n_noise_ops, int ntheta_noise,
                         int device, gogp_handle** out);
 void gogp_destroy(gogp_handle* h);
+
+/* The event table of tutorial/events' Simil{Events} (tutorial/events/kernel/kernel.go:10-12): n rows of
+ * (from, to, discount), n <= 16, used by GOGP_OP_EVENTS leaves. */
+gogp_status gogp_set_events(gogp_handle* h, const double* events, int n);
 
 /* Assigning the fields gp.X, gp.Y (tutorial/tutorial.go:114-115) for the
  * hyper-parameters-only mode of Observe.  X is N x ndim row-major. */

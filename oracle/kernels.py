@@ -140,6 +140,28 @@ class AnynoiseNoise:
         return ad.Dual(1e-5)
 
 
+class EventsSimil:
+    """tutorial/events/kernel/kernel.go:10-46: scaled Matern52, discounted when the pair straddles
+    an event boundary (first matching event only)."""
+    ntheta = 2
+
+    def __init__(self, events):
+        self.events = [tuple(float(v) for v in e) for e in events]
+
+    def observe(self, x):
+        import numpy as np
+        k = x[0] * Matern52.observe(x[1:])
+        xa, xb = np.asarray(x[2].v), np.asarray(x[3].v)
+        lo, hi = np.minimum(xa, xb), np.maximum(xa, xb)
+        factor = np.ones(np.broadcast(lo, hi).shape)
+        done = np.zeros(factor.shape, dtype=bool)
+        for (frm, to, disc) in self.events:
+            hit = ((lo < frm) & (frm <= hi)) | ((lo < to) & (to <= hi))
+            factor = np.where(hit & ~done, disc, factor)
+            done |= hit
+        return k * ad.Dual(factor)
+
+
 # --- synthetic benchmark kernels (SURVEY.md section 8 d; not in the reference) ---
 class ScaledNormal1D:
     """C2: theta0 * Normal(l)."""

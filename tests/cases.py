@@ -53,6 +53,8 @@ CASES = {
     "c3_ard8": (8, ard_normal_periodic(8), k.UniformNoise, ok.ArdNormalTimesPeriodic(8), ok.UniformNoise),
     "c3_ard3": (3, ard_normal_periodic(3), k.UniformNoise, ok.ArdNormalTimesPeriodic(3), ok.UniformNoise),
     "c5_matern4": (4, ard_matern32(4), k.UniformNoise, ok.ArdMatern32(4), ok.UniformNoise),
+    "events": (1, k.Param(0) * k.Matern52.Of(l=1) * k.Events([(1.0, 2.5, 0.3), (3.0, 6.0, 0.5)]), 0.01 * k.UniformNoise,
+               ok.EventsSimil([(1.0, 2.5, 0.3), (3.0, 6.0, 0.5)]), ok.ScaledUniformNoise(0.01)),
     "sum_times": (1, (k.Param(0) * k.Normal.Of(l=1) + k.Param(2)) * k.Matern32.Of(l=3), k.UniformNoise,
                   _Sum2(), ok.UniformNoise),
 }
@@ -76,7 +78,7 @@ def synth(name, N, seed=0, spread=None):
     if name == "hyperpriors":
         logt[4] += np.log(0.3)  # period 10*theta4 ~ 3
     if ntn and name not in ("anynoise",):
-        scale = 0.01 if name in ("barebones", "hyperpriors", "warpedtime") else 1.0
+        scale = 0.01 if name in ("barebones", "hyperpriors", "warpedtime", "events") else 1.0
         logt[nts] = 0.5 * np.log(0.01 / scale) + 0.05 * rng.standard_normal()  # noise variance ~1e-2
     return X, y, logt
 

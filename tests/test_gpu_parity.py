@@ -115,7 +115,7 @@ def test_hyper_only_parity(name, N):
     assert np.max(np.abs(sigma ** 2 - sref ** 2)) <= PRED_TOL * max(1.0, np.abs(sref).max() ** 2)
 
 
-@pytest.mark.parametrize("name", ["normal_uniform", "anynoise", "warpedtime", "hyperpriors", "c3_ard3", "c5_matern4"])
+@pytest.mark.parametrize("name", ["normal_uniform", "anynoise", "warpedtime", "hyperpriors", "events", "c3_ard3", "c5_matern4"])
 @pytest.mark.parametrize("N", [1, 3, 43, 150])
 def test_with_obs_parity(name, N):
     """Observe's [theta | X | Y] layout: gradient w.r.t. inputs and outputs too
@@ -146,7 +146,7 @@ def test_barebones_kat():
     assert np.allclose(g.Gradient(), [-0.1009289296, 2.3769085404, -7.5447626235], atol=1e-8)
 
 
-@pytest.mark.parametrize("name", ["barebones", "hyperpriors", "anynoise", "warpedtime"])
+@pytest.mark.parametrize("name", ["barebones", "hyperpriors", "anynoise", "warpedtime", "events"])
 def test_tutorial_expanding_window(name):
     """tutorial.Evaluate's loop shape (tutorial/tutorial.go:91-179): N = 0..len-1 on the
     shipped data, one Observe+Gradient and a one-step forecast per prefix."""
