@@ -161,6 +161,8 @@ class BlockCyclicCholesky:
         self.logdet2 = backend.zeros(2)
         self.sumlog = backend.zeros(1)
         self.factored = False
+        import os
+        self.diag_after_bulk = os.environ.get("GOGP_DIAG_AFTER_BULK", "1") == "1"
 
     def owner(self, I, J):
         return (I % self.Pr) * self.Pc + (J % self.Pc)
@@ -241,10 +243,16 @@ class BlockCyclicCholesky:
                 i0, j = self.ri[mine[0]], self.ci[k + 1]
                 be.gemm(self.local[i0 * NB:(i0 + len(mine)) * NB, j * NB:(j + 1) * NB], mypanel, pcm[:NB], -1.0, 1.0)
                 first = 1
-            # block (k+1, k+1) is final now: its owner factors it BEFORE queueing the bulk update,
-            # whose CTAs would otherwise keep every SM too full for the 135 KB leaf kernel
-            self._factor_diag(k + 1)
+            # block (k+1, k+1) is final now.  Its owner factors it on the priority main stream while
+            # the bulk update runs on the side stream (diag_after_bulk, default): the TMA GEMM keeps one
+            # 197 KB CTA per SM, so every CTA that retires frees a whole SM for the 135 KB leaf kernel
+            # (measured on 1 GPU, N = 32768: 426 -> 399 ms).  With the 2-CTA/SM cp.async GEMM the leaf
+            # starved behind 90 KB CTAs and factoring BEFORE queueing the bulk was faster (GOGP_DIAG_AFTER_BULK=0).
+            if not self.diag_after_bulk:
+                self._factor_diag(k + 1)
             if not mine or not cols:
+                if self.diag_after_bulk:
+                    self._factor_diag(k + 1)
                 continue
             base = self._first_after(self.r, k)
 
@@ -263,6 +271,8 @@ class BlockCyclicCholesky:
                 be.side(bulk)
             else:
                 bulk()
+            if self.diag_after_bulk:
+                self._factor_diag(k + 1)
         be.wait_side()
         self.factored = True
 
