@@ -343,3 +343,21 @@ def test_full_size_properties_n32768():
     lml_bc = ch.solve_lml(y)
     be.close()
     assert abs(lml_bc - lml) <= 1e-11 * max(abs(lml), N), (lml_bc, lml)
+
+
+def test_produce_chunks_many_test_points():
+    """Produce walks the test points in chunks of 8192: M = 9000 crosses a chunk boundary."""
+    name, N, M = "c2_rbf", 500, 9000
+    X, y, logt = cases.synth(name, N, seed=12)
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    dg.Observe(logt.copy())
+    og.observe(logt.copy())
+    Z = np.random.default_rng(4).uniform(X.min() - 1, X.max() + 1, size=(M, 1))
+    mu, sigma, err = dg.Produce(Z)
+    assert err is None and len(mu) == M
+    mref, sref = og.produce(Z, clamp=True)
+    assert np.max(np.abs(mu - mref)) <= PRED_TOL * max(1.0, np.abs(mref).max())
+    assert np.max(np.abs(sigma ** 2 - sref ** 2)) <= PRED_TOL * max(1.0, np.abs(sref).max() ** 2)
