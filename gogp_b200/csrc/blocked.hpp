@@ -71,6 +71,55 @@ struct Blocked {
         potrf(o + n1, n2);
     }
 
+    // Right-looking factorisation over block columns with one step of look-ahead, nested:
+    // level 0 cuts the matrix into la_nb[0]-wide block columns (2048), level 1 cuts each of
+    // their diagonal blocks into la_nb[1]-wide ones, ... down to 128 = one leaf each; a level
+    // whose width is 0 or too wide for the block at hand (n < 3 nb) is skipped.  The recursion above
+    // leaves the GPU nearly idle while a diagonal block is factored (a chain of one-CTA leaf
+    // kernels and K = 128 updates).  Here, per level, with P = panel solve, U1d / U1b = update of
+    // the next diagonal block / of the rows below it, U2 = rest of the trailing update, D = the
+    // next diagonal block's factorisation (one level down):
+    //   current stream:  P_k  [wait U2_k-1]  U1d_k  D_k+1  [wait U1b_k]  P_k+1 ...
+    //   bulk stream   :       [after P_k]    U1b_k  U2_k                 U1b_k+1  U2_k+1 ...
+    // U1d/U1b write block column k+1, U2 the columns right of it: disjoint, all read P_k only.
+    // Same flops as the recursion; the la_* hooks are no-ops for a backend without streams
+    // (then this is a plain right-looking sweep).  Level l's bulk stream must outrank level
+    // l-1's, and the current stream both.
+    static constexpr int kLaLevels = 3;
+    int64_t la_nb[kLaLevels] = {0, 0, 0};
+
+    void potrf_la(int64_t o0, int64_t n, int lvl) {
+        const int64_t nb = lvl < kLaLevels ? la_nb[lvl] : 0;
+        if (nb < kTile || nb % kTile || n < 3 * nb) {
+            if (lvl + 1 < kLaLevels)
+                potrf_la(o0, n, lvl + 1);
+            else
+                potrf(o0, n);
+            return;
+        }
+        const int64_t end = o0 + n;
+        potrf_la(o0, nb, lvl + 1);
+        for (int64_t o = o0; o + nb < end; o += nb) {
+            const int64_t r0 = o + nb, m = end - r0, w1 = m < nb ? m : nb, m2 = m - w1;
+            double* P = at(A, r0, o);
+            trsm(P, ld, m, o, nb);
+            be.la_fork(lvl);       // the bulk stream may start once the panel is solved
+            be.la_wait_bulk(lvl);  // step k-1's bulk update wrote the block U1d touches
+            be.gemm(at(A, r0, r0), ld, P, ld, P, ld, w1, w1, nb, -1.0, 1.0, BL_LOWER, nullptr);
+            if (m2 > 0) {
+                double* P2 = at(A, r0 + w1, o);
+                be.la_bulk_begin(lvl);
+                be.gemm(at(A, r0 + w1, r0), ld, P2, ld, P, ld, m2, w1, nb, -1.0, 1.0, BL_FULL, nullptr);
+                be.la_mark_below(lvl);
+                be.gemm(at(A, r0 + w1, r0 + w1), ld, P2, ld, P2, ld, m2, m2, nb, -1.0, 1.0, BL_LOWER, nullptr);
+                be.la_bulk_end(lvl);
+            }
+            potrf_la(r0, w1, lvl + 1);
+            be.la_wait_below(lvl);  // the next panel solve reads the rows U1b wrote
+        }
+        be.la_wait_bulk(lvl);
+    }
+
     // B (m x n, ldb) <- B L^-T with L = A[o:o+n, o:o+n]
     void trsm(double* B, int64_t ldb, int64_t m, int64_t o, int64_t n) {
         if (n == kTile) {

@@ -44,6 +44,21 @@ inline int64_t par_block() {
     }
     return v;
 }
+// Block-column widths of the nested look-ahead factorisation (Blocked::potrf_la), outermost first;
+// "0": plain recursion on one stream.  Read per call: the parity tests switch it in-process.
+inline void la_blocks(int64_t (&nb)[3]) {
+    const char* e = getenv("GOGP_LA_NB");
+    nb[0] = 2048;
+    nb[1] = 0;
+    nb[2] = 128;
+    if (!e) return;
+    nb[0] = nb[1] = nb[2] = 0;
+    for (int i = 0; i < 3 && *e; ++i) {
+        nb[i] = atoll(e);
+        while (*e && *e != ',') ++e;
+        if (*e == ',') ++e;
+    }
+}
 // The column-wise inverse measured slower than the recursion (potri 722 -> 728 ms at 2048): off by default.
 inline int64_t cols_max() {
     static int64_t v = -1;
@@ -118,6 +133,43 @@ struct CudaBackend {
         }
     }
     void set_scratch_row(int64_t r) { scratch_row = r; }
+    // look-ahead (Blocked::potrf_la): `s` is the priority stream, bulk[l] the stream of level l's
+    // trailing updates (priority rising with l, all below `s`)
+    struct LaLevel {
+        cudaStream_t bulk = nullptr;
+        cudaEvent_t fork = nullptr, below = nullptr, done = nullptr;
+        cudaStream_t saved = nullptr;
+        bool pending = false, below_pending = false;
+    };
+    LaLevel* la = nullptr;  // kLaLevels entries, or null: everything on `s`
+    void la_fork(int l) {
+        if (la) cudaEventRecord(la[l].fork, s);
+    }
+    void la_bulk_begin(int l) {
+        if (!la) return;
+        cudaStreamWaitEvent(la[l].bulk, la[l].fork, 0);
+        la[l].saved = s;
+        s = la[l].bulk;
+    }
+    void la_mark_below(int l) {
+        if (!la) return;
+        cudaEventRecord(la[l].below, s);
+        la[l].below_pending = true;
+    }
+    void la_bulk_end(int l) {
+        if (!la) return;
+        cudaEventRecord(la[l].done, s);
+        s = la[l].saved;
+        la[l].pending = true;
+    }
+    void la_wait_bulk(int l) {
+        if (la && la[l].pending) cudaStreamWaitEvent(s, la[l].done, 0);
+        if (la) la[l].pending = false;
+    }
+    void la_wait_below(int l) {
+        if (la && la[l].below_pending) cudaStreamWaitEvent(s, la[l].below, 0);
+        if (la) la[l].below_pending = false;
+    }
     void gemm(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m, int64_t n,
               int64_t k, double alpha, double beta, int mode, double* cdiag) {
         const bool p = prof && prof->on;
@@ -192,6 +244,7 @@ struct gogp_handle {
     cudaStream_t side[kParStreams] = {nullptr};
     cudaEvent_t side_ev[kParStreams] = {nullptr};
     cudaEvent_t fork_ev = nullptr;
+    CudaBackend::LaLevel la[3];  // streams / events of the look-ahead factorisation
     int64_t launches = 0;
     GemmProfile prof;
 };
@@ -343,7 +396,13 @@ gogp_status absorb(gogp_handle* h) {
 
     CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
     Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
-    bl.potrf(0, Npad);
+    // per-launch accounting needs launches that do not overlap: profile on one stream
+    la_blocks(bl.la_nb);
+    if (!h->prof.on) {
+        for (auto& l : h->la) l.pending = l.below_pending = false;
+        be.la = h->la;
+    }
+    bl.potrf_la(0, Npad, 0);
     CK(cudaEventRecord(h->ev[2], s));
 
     // alpha = L^-T (L^-1 y)
@@ -415,7 +474,19 @@ gogp_status gogp_create(int ndim, const gogp_op* simil, int n_simil_ops, int nth
         return fail(h, GOGP_CUDA_ERROR, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (device < 0 || device >= count) return fail(h, GOGP_BAD_ARGUMENT, "device index out of range");
     CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // the handle's stream outranks the bulk stream: the latency-bound chain of the next block
+    // column gets every SM it asks for while the trailing update fills the rest
+    int prio_least = 0, prio_greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest));
+    for (int l = 0; l < 3; ++l) {
+        int prio = prio_least - l;  // numerically lower = higher priority
+        if (prio <= prio_greatest) prio = prio_greatest < prio_least ? prio_greatest + 1 : prio_least;
+        CK(cudaStreamCreateWithPriority(&h->la[l].bulk, cudaStreamNonBlocking, prio));
+        CK(cudaEventCreateWithFlags(&h->la[l].fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->la[l].below, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->la[l].done, cudaEventDisableTiming));
+    }
     for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
     for (auto& st : h->side) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& ev : h->side_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -446,6 +517,12 @@ void gogp_destroy(gogp_handle* h) {
     for (auto& ev : h->side_ev)
         if (ev) cudaEventDestroy(ev);
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+    for (auto& l : h->la) {
+        if (l.fork) cudaEventDestroy(l.fork);
+        if (l.below) cudaEventDestroy(l.below);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.bulk) cudaStreamDestroy(l.bulk);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -85,6 +85,12 @@ struct HostBackend {
     void par_use(int) {}
     void par_end() {}
     void set_scratch_row(int64_t) {}
+    void la_fork(int) {}
+    void la_bulk_begin(int) {}
+    void la_mark_below(int) {}
+    void la_bulk_end(int) {}
+    void la_wait_bulk(int) {}
+    void la_wait_below(int) {}
     void trtri_leaf(const double* winv, double* dst, int64_t ld) {
         const int n = (int)kTile;
         for (int r = 0; r < n; ++r)
@@ -106,6 +112,17 @@ int cpu_blocked_potrf(double* A, int64_t n, double* winv) {
     HostBackend be;
     Blocked<HostBackend> bl{be, A, n, winv, g_rl_max, g_rl_max};
     bl.potrf(0, n);
+    return be.info;
+}
+
+// The look-ahead (flat right-looking) factorisation with nb-wide block columns.
+int cpu_blocked_potrf_la(double* A, int64_t n, double* winv, int64_t nb0, int64_t nb1, int64_t nb2) {
+    HostBackend be;
+    Blocked<HostBackend> bl{be, A, n, winv, g_rl_max, g_rl_max};
+    bl.la_nb[0] = nb0;
+    bl.la_nb[1] = nb1;
+    bl.la_nb[2] = nb2;
+    bl.potrf_la(0, n, 0);
     return be.info;
 }
 

@@ -256,6 +256,38 @@ def test_factor_and_inverse_residuals_4096():
     assert np.max(np.abs(sigma ** 2 - sref ** 2)) <= PRED_TOL
 
 
+@pytest.mark.parametrize("nb", ["256", "512,0,128", "0,0,128", "640,256,128", "384,128"])
+def test_lookahead_factorisation_matches_recursion_and_oracle(nb, monkeypatch):
+    """Blocked::potrf_la (nested block columns of widths GOGP_LA_NB, next column on the priority
+    stream, bulk updates on lower-priority streams) against the one-stream recursion and the oracle;
+    repeated runs must be bit-identical (a missing cross-stream dependency shows up as a changing
+    result)."""
+    import ctypes as C
+    from gogp_b200 import _lib
+    N = 2000  # Npad = 2048 >= 3 nb
+    X, y, logt = cases.synth("c2_rbf", N, seed=4)
+    og = cases.make_oracle_gp("c2_rbf")
+    og.X, og.Y = X, y
+    ref = og.observe(logt.copy())
+    gref = og.gradient()
+    out = {}
+    for mode in ("0", nb, nb, nb, nb):
+        monkeypatch.setenv("GOGP_LA_NB", mode)
+        dg = cases.make_device_gp("c2_rbf")
+        dg.X, dg.Y = X, y
+        lml = dg.Observe(logt.copy())
+        g = dg.Gradient()
+        Lm = np.zeros((N, N))
+        assert _lib.lib().gogp_get_factor(dg._handle(), _lib.dptr(Lm), N) == _lib.OK
+        assert abs(lml - ref) <= LML_TOL * max(abs(ref), N)
+        assert _grad_err(g, gref) <= GRAD_TOL
+        assert np.linalg.norm(Lm @ Lm.T - og.K) / np.linalg.norm(og.K) < 1e-13
+        if mode in out:
+            assert lml == out[mode][0] and np.array_equal(Lm, out[mode][1])
+        out[mode] = (lml, Lm)
+    assert np.abs(out["0"][1] - out[nb][1]).max() < 1e-11
+
+
 def test_repeatable_and_handle_reuse():
     """Same inputs -> bit-identical results (fixed reduction orders); a handle survives
     growing and shrinking N."""

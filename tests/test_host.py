@@ -121,6 +121,28 @@ def test_blocked_recursion_on_host_backend(cpu_blocked, n, rl_max):
     assert np.abs(B - sla.solve_triangular(Lref, B0.T, lower=True).T).max() < 1e-12
 
 
+@pytest.mark.parametrize("n,nb,nb1,nb2", [(384, 128, 0, 0), (640, 128, 0, 0), (640, 256, 0, 0), (896, 256, 0, 0),
+                                          (256, 128, 0, 0), (1280, 384, 128, 0), (1536, 512, 0, 128),
+                                          (1024, 0, 128, 0), (640, 0, 0, 0), (2304, 768, 256, 128)])
+def test_blocked_lookahead_factorisation_on_host_backend(cpu_blocked, n, nb, nb1, nb2):
+    """Blocked::potrf_la (nested block columns, next column first) gives the same factor."""
+    cpu_blocked.cpu_blocked_set_rl_max(C.c_int64(256))
+    cpu_blocked.cpu_blocked_potrf_la.restype = C.c_int
+    rng = np.random.default_rng(n + nb)
+    G = rng.standard_normal((n, n))
+    K = G @ G.T / n + np.eye(n)
+    A = K.copy()
+    winv = np.zeros((n // 128, 128, 128))
+    cpu_blocked.cpu_blocked_potrf_la.argtypes = [C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double)] + [C.c_int64] * 3
+    assert cpu_blocked.cpu_blocked_potrf_la(_p(A), C.c_int64(n), _p(winv), C.c_int64(nb), C.c_int64(nb1),
+                                            C.c_int64(nb2)) == 0
+    Lref = np.linalg.cholesky(K)
+    assert np.abs(np.tril(A) - Lref).max() < 1e-13
+    for t in range(n // 128):
+        d = Lref[t * 128:(t + 1) * 128, t * 128:(t + 1) * 128]
+        assert np.abs(winv[t] @ d - np.eye(128)).max() < 1e-12
+
+
 def test_blocked_potrf_flags_non_pd(cpu_blocked):
     cpu_blocked.cpu_blocked_set_rl_max(C.c_int64(0))
     n = 256
