@@ -26,7 +26,7 @@ SYMBOLS = (
     "gogp_create", "gogp_destroy", "gogp_set_events", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_lml",
     "gogp_produce", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
-    "gogp_debug_gemm", "gogp_debug_leaf", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
+    "gogp_debug_gemm", "gogp_debug_leaf", "gogp_debug_leaf_run", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
     "gogp_dev_gemm", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
 )
 
@@ -109,6 +109,8 @@ def lib():
         f.restype = C.c_int
     L.gogp_debug_leaf.argtypes = [H, C.c_int, C.c_int, dp]
     L.gogp_debug_leaf.restype = C.c_int
+    L.gogp_debug_leaf_run.argtypes = [H, C.c_int, dp, dp, dp, C.POINTER(C.c_int)]
+    L.gogp_debug_leaf_run.restype = C.c_int
     L.gogp_timer_start.argtypes = [H]
     L.gogp_timer_start.restype = C.c_int
     L.gogp_timer_stop.argtypes = [H, dp]

@@ -865,11 +865,33 @@ gogp_status gogp_debug_leaf(gogp_handle* h, int variant, int iters, double* usec
         }
         if (total < best) best = total;
     }
-    set_leaf_variant(0);
+    set_leaf_variant(-1);  // back to the default (GOGP_LEAF or the blocked kernel)
     cudaFree(A);
     cudaFree(W);
     CK(cudaGetLastError());
     *usec = best / iters * 1e3;
+    return GOGP_OK;
+}
+
+gogp_status gogp_debug_leaf_run(gogp_handle* h, int variant, const double* A, double* L, double* W, int* info) {
+    if (!h || !A || !L || !W || !info) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    double* d = nullptr;
+    const size_t bytes = (size_t)TILE * TILE * sizeof(double);
+    CK(cudaMalloc(&d, 2 * bytes));
+    set_leaf_variant(variant);
+    cudaMemsetAsync(h->dInfo, 0, sizeof(int), h->stream);
+    cudaMemcpyAsync(d, A, bytes, cudaMemcpyHostToDevice, h->stream);
+    launch_potrf_leaf(d, TILE, d + TILE * TILE, h->dInfo, 0, h->stream);
+    cudaMemcpyAsync(L, d, bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(W, d + TILE * TILE, bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(info, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    set_leaf_variant(-1);  // back to the default (GOGP_LEAF or the blocked kernel)
+    cudaFree(d);
+    ++h->launches;
+    if (e != cudaSuccess) return fail(h, GOGP_CUDA_ERROR, cudaGetErrorString(e));
+    CK(cudaGetLastError());
     return GOGP_OK;
 }
 

@@ -3,6 +3,7 @@
 // (gp/gp.go:232-236), log-determinant and y.alpha (gp/gp.go:250-251), and small
 // reductions used by Produce (gp/gp.go:335-357).
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -12,6 +13,8 @@ namespace {
 
 constexpr int LP = 132;  // smem pitch (doubles), = 4 mod 16: a half-warp = 4 rows x 4 k-phases hits 16 distinct 8-byte banks
 
+// First version of the tile kernel (kept selectable, set_leaf_variant(1) / GOGP_LEAF=1, as the
+// timing baseline): 150 us per tile, bound by one CTA-wide barrier per column.
 // Cholesky (Crout, column by column) of one 128x128 tile held in shared memory,
 // fused with the inverse W = L^-1 built row by row one step behind: at step j
 // the threads of rows r >= j form column j of L (dot products of rows r and j
@@ -19,9 +22,9 @@ constexpr int LP = 132;  // smem pitch (doubles), = 4 mod 16: a half-warp = 4 ro
 // form row j-1 of W,  W[j-1][r] = -(sum_{k=r}^{j-2} L[j-1][k] W[k][r]) / L[j-1][j-1].
 // Four threads share a row and split k by k mod 4; one barrier per column.
 // W[i][c] (c <= i) lives at S[c][i+1], the unused upper triangle of the array.
-__global__ void __launch_bounds__(512, 1) potrf_leaf_kernel(double* __restrict__ A, int64_t ld,
-                                                            double* __restrict__ winv, int* __restrict__ info,
-                                                            int base) {
+__global__ void __launch_bounds__(512, 1) potrf_leaf_crout_kernel(double* __restrict__ A, int64_t ld,
+                                                                  double* __restrict__ winv, int* __restrict__ info,
+                                                                  int base) {
     extern __shared__ double S[];  // [128][LP]
     __shared__ double adiag[TILE];
     const int tid = threadIdx.x;
@@ -89,6 +92,247 @@ __global__ void __launch_bounds__(512, 1) potrf_leaf_kernel(double* __restrict__
         const int rr = idx >> 7, c = idx & 127;
         A[(int64_t)rr * ld + c] = (c <= rr) ? S[rr * LP + c] : 0.0;
         winv[idx] = (c <= rr) ? S[c * LP + rr + 1] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void dmma_leaf(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int MP = 100;  // pitch of the 32 x 96 side buffer: rows 32 B apart mod 128 B, like LP
+constexpr int WS = 1;    // W[i][c] (c <= i) lives at S[c][i + WS], the unused upper triangle
+
+constexpr int LEAF_THREADS = 384;  // 12 warps: 170 registers each, no spills in the register-resident phases
+// Blocked tile kernel: Cholesky of one 128x128 tile and its inverse W = L^-1, by 32-column
+// blocks so that the serial part never meets a CTA-wide barrier.  Per block b (o = 32 b):
+//   A  warp 0, registers: lane i holds row i of the 32x32 diagonal block; right-looking,
+//      column by column, pivot and column broadcast by warp shuffles (no barrier);
+//   B  warp 0: Wd = D^-1, lane c solves D w = e_c forward (rows of D broadcast from smem);
+//   C  panel below:  X = P Wd^T                                   (DMMA, 16-row warp tiles)
+//   E1 M = -Wd L[b, 0:o]  into the side buffer                     (DMMA)
+//   D  trailing update:  A22 -= X X^T, lower 16x16 warp tiles       (DMMA)
+//   E2 block row b of the inverse:  W[b, j] = sum_{k=j}^{b-1} M[:, k] W[k, j]   (DMMA)
+// C/E1 and D/E2 are independent pairs and share a phase; three CTA barriers per block.
+// Fragment convention as in dgemm.cu: a = A[row fr + 8i][k fk], b = B[col fr + 8j][k fk],
+// acc = C[row fr + 8i][col 2 fk + 8j + {0,1}], fr = lane >> 2, fk = lane & 3.
+__global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, int64_t ld,
+                                                            double* __restrict__ winv, int* __restrict__ info,
+                                                            int base) {
+    extern __shared__ __align__(16) double S[];  // [128][LP], then the side buffer [32][MP]
+    double* Mb = S + TILE * LP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    for (int idx = tid; idx < TILE * (LP / 2); idx += LEAF_THREADS) {
+        const int r = idx / (LP / 2), c2 = (idx - r * (LP / 2)) * 2;
+        double2 v = make_double2(0.0, 0.0);
+        if (c2 <= r) {
+            v = *reinterpret_cast<const double2*>(A + (int64_t)r * ld + c2);
+            if (c2 + 1 > r) v.y = 0.0;
+        }
+        *reinterpret_cast<double2*>(S + r * LP + c2) = v;
+    }
+    __syncthreads();
+
+    for (int b = 0; b < 4; ++b) {
+        const int o = 32 * b;
+        if (warp == 0) {
+            // ---- A: diagonal block in registers ----
+            double a[32];
+            {
+                const double* row = S + (o + lane) * LP + o;
+#pragma unroll
+                for (int k = 0; k < 32; k += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(row + k);
+                    a[k] = v.x;
+                    a[k + 1] = v.y;
+                }
+            }
+            double rinv = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                double d = __shfl_sync(FULL, a[j], j);
+                if (!(d > 0.0)) {  // not positive definite (or NaN): flag, keep going
+                    if (lane == j) atomicCAS(info, 0, base + o + j + 1);
+                    d = 1.0;
+                }
+                const double rs = rsqrt(d);
+                const double l = (lane == j ? d : a[j]) * rs;  // one reciprocal square root, no divide
+                a[j] = l;
+                if (lane == j) rinv = rs;
+#pragma unroll
+                for (int k = j + 1; k < 32; ++k) {
+                    const double lk = __shfl_sync(FULL, l, k);
+                    a[k] = fma(-l, lk, a[k]);
+                }
+            }
+            {
+                double* row = S + (o + lane) * LP + o;
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (k <= lane) row[k] = a[k];
+            }
+            __syncwarp();
+            // ---- B: inverse of the diagonal block, one column per lane ----
+            double t[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const double rk = __shfl_sync(FULL, rinv, k);
+                t[k] *= rk;
+#pragma unroll
+                for (int i = k + 1; i < 32; ++i) t[i] = fma(-S[(o + i) * LP + o + k], t[k], t[i]);
+            }
+            {
+                double* row = S + (o + lane) * LP + o + WS;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i >= lane) row[i] = t[i];
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: C (panel solve) and E1 (scaled block row) ----
+        const int nC = (96 - o) / 16, nE1 = 2 * b;
+        for (int task = warp; task < nC + nE1; task += LEAF_THREADS / 32) {
+            if (task < nC) {
+                const int r0 = o + 32 + 16 * task;
+                double acc[2][4][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const int k = 4 * ks + fk;
+                    double av[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) av[i] = S[(r0 + fr + 8 * i) * LP + o + k];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (ks > 2 * j + 1) continue;  // Wd[c][k] = 0 for k > c
+                        const int c = 8 * j + fr;
+                        double bv = S[(o + k) * LP + o + c + WS];
+                        if (ks >= 2 * j && k > c) bv = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) dmma_leaf(acc[i][j][0], acc[i][j][1], av[i], bv);
+                    }
+                }
+                __syncwarp();  // every lane has read its rows of P before X replaces them
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<double2*>(S + (r0 + fr + 8 * i) * LP + o + 8 * j + 2 * fk) =
+                            make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
+                const int te = task - nC;
+                const int i0 = 16 * (te & 1), q0 = 32 * (te >> 1);
+                double acc[2][4][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                for (int ks = 0; 4 * ks <= i0 + 15; ++ks) {  // Wd[i][m] = 0 for m > i
+                    const int m = 4 * ks + fk;
+                    double av[2], bv[4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int ii = i0 + fr + 8 * i;
+                        av[i] = (m <= ii) ? S[(o + m) * LP + o + ii + WS] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bv[j] = S[(o + m) * LP + q0 + fr + 8 * j];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma_leaf(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<double2*>(Mb + (i0 + fr + 8 * i) * MP + q0 + 8 * j + 2 * fk) =
+                            make_double2(-acc[i][j][0], -acc[i][j][1]);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: D (trailing update) and E2 (block row b of the inverse) ----
+        const int nt = (96 - o) / 16, nD = nt * (nt + 1) / 2, nE2 = 4 * b;
+        for (int task = warp; task < nD + nE2; task += LEAF_THREADS / 32) {
+            double acc[2][2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            if (task < nD) {
+                int ti = 0, p = task;
+                while (p > ti) {
+                    p -= ti + 1;
+                    ++ti;
+                }
+                const int r0 = o + 32 + 16 * ti, c0 = o + 32 + 16 * p;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const int k = o + 4 * ks + fk;
+                    double av[2], bv[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) av[i] = S[(r0 + fr + 8 * i) * LP + k];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) bv[j] = S[(c0 + fr + 8 * j) * LP + k];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dmma_leaf(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int row = r0 + fr + 8 * i, col = c0 + 8 * j + 2 * fk + e;
+                            if (col <= row) S[row * LP + col] -= acc[i][j][e];  // above the diagonal lives W
+                        }
+            } else {
+                const int te = task - nD;
+                const int jb = te >> 2, i0 = 16 * ((te >> 1) & 1), c0 = 32 * jb + 16 * (te & 1);
+                for (int q0 = c0; q0 < o; q0 += 4) {  // W[q][cc] = 0 for q < cc
+                    const int q = q0 + fk;
+                    double av[2], bv[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) av[i] = Mb[(i0 + fr + 8 * i) * MP + q];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int cc = c0 + fr + 8 * j;
+                        bv[j] = (q >= cc) ? S[cc * LP + q + WS] : 0.0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dmma_leaf(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            S[(c0 + 8 * j + 2 * fk + e) * LP + o + i0 + fr + 8 * i + WS] = acc[i][j][e];
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
+        const int rr = idx >> 7, c = idx & 127;
+        A[(int64_t)rr * ld + c] = (c <= rr) ? S[rr * LP + c] : 0.0;
+        winv[idx] = (c <= rr) ? S[c * LP + rr + WS] : 0.0;
     }
 }
 
@@ -319,18 +563,28 @@ void launch_fill_pattern(double* v, int64_t n, cudaStream_t s) {
     if (n > 0) fill_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(v, n, 0.0, 1);
 }
 
-void set_leaf_variant(int) {}  // kept for gogp_debug_leaf; the shipped kernel has one variant
+static int g_leaf_variant = -1;  // 0: blocked kernel (shipped), 1: first version (Crout, one barrier per column)
+void set_leaf_variant(int v) { g_leaf_variant = v; }
 
 void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s) {
-    const size_t smem = (size_t)TILE * LP * sizeof(double);
+    if (g_leaf_variant < 0) {
+        const char* e = getenv("GOGP_LEAF");
+        g_leaf_variant = e ? atoi(e) : 0;
+    }
+    const size_t smem_crout = (size_t)TILE * LP * sizeof(double);
+    const size_t smem = ((size_t)TILE * LP + 32 * MP) * sizeof(double);
     static bool configured[64] = {false};  // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(potrf_leaf_crout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_crout);
         cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev & 63] = true;
     }
-    potrf_leaf_kernel<<<1, 512, smem, s>>>(A, ld, winv, info, base);
+    if (g_leaf_variant == 1)
+        potrf_leaf_crout_kernel<<<1, 512, smem_crout, s>>>(A, ld, winv, info, base);
+    else
+        potrf_leaf_kernel<<<1, LEAF_THREADS, smem, s>>>(A, ld, winv, info, base);
 }
 
 void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t s) {

@@ -219,9 +219,13 @@ gogp_status gogp_debug_build(gogp_handle* h, const double* theta_simil, const do
  * (mma.sync m8n8k4 f64), 1 DFMA.  Returns TFLOP/s in *tflops. */
 gogp_status gogp_debug_fp64_peak(gogp_handle* h, int which, double* tflops);
 
-/* Device time of the 128 x 128 tile Cholesky+inverse kernel in microseconds (variant 0; other
- * variants leave parts out and exist to attribute its time). */
+/* Device time of the 128 x 128 tile Cholesky+inverse kernel in microseconds (variant 0: the
+ * shipped blocked kernel; 1: the first, column-by-column version kept as the timing baseline). */
 gogp_status gogp_debug_leaf(gogp_handle* h, int variant, int iters, double* usec);
+
+/* Test hook for the tile kernel alone: A (128 x 128 row-major, lower used) -> L (lower, upper
+ * zeroed) and W = L^-1 (lower); *info = 0 or the 1-based index of the first non-positive pivot. */
+gogp_status gogp_debug_leaf_run(gogp_handle* h, int variant, const double* A, double* L, double* W, int* info);
 
 /* One C -= A B^T of size n (tiles of the trailing update), timed; returns
  * TFLOP/s.  mode 0 full, 1 lower-triangular (SYRK). */

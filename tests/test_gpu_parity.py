@@ -288,6 +288,35 @@ def test_lookahead_factorisation_matches_recursion_and_oracle(nb, monkeypatch):
     assert np.abs(out["0"][1] - out[nb][1]).max() < 1e-11
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_tile_kernel_against_numpy(variant):
+    """The 128 x 128 tile kernel alone (blocked shipped version and the first version): factor,
+    inverse, and the index of the first bad pivot."""
+    import ctypes as C
+    from gogp_b200 import _lib
+    dg = cases.make_device_gp("c2_rbf")
+    h = dg._handle()
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    for trial in range(4):
+        G = rng.standard_normal((128, 128))
+        K = G @ G.T / 128 + np.eye(128) * (10.0 ** -trial)
+        A = np.tril(K) + np.triu(rng.standard_normal((128, 128)), 1)  # the upper triangle must be ignored
+        Lo, Wo, info = np.zeros((128, 128)), np.zeros((128, 128)), C.c_int(-1)
+        assert L.gogp_debug_leaf_run(h, variant, _lib.dptr(A), _lib.dptr(Lo), _lib.dptr(Wo), C.byref(info)) == _lib.OK
+        ref = np.linalg.cholesky(K)
+        assert info.value == 0
+        assert np.abs(Lo - ref).max() <= 1e-13 * np.abs(ref).max() * np.linalg.cond(ref)
+        assert np.abs(np.triu(Lo, 1)).max() == 0.0 and np.abs(np.triu(Wo, 1)).max() == 0.0
+        assert np.abs(Wo @ ref - np.eye(128)).max() <= 1e-13 * np.linalg.cond(ref) ** 2
+    for bad in (0, 31, 32, 77, 127):
+        K = np.eye(128) * 2.0
+        K[bad, bad] = -1.0
+        Lo, Wo, info = np.zeros((128, 128)), np.zeros((128, 128)), C.c_int(-1)
+        assert L.gogp_debug_leaf_run(h, variant, _lib.dptr(K), _lib.dptr(Lo), _lib.dptr(Wo), C.byref(info)) == _lib.OK
+        assert info.value == bad + 1
+
+
 def test_repeatable_and_handle_reuse():
     """Same inputs -> bit-identical results (fixed reduction orders); a handle survives
     growing and shrinking N."""
