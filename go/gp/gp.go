@@ -293,3 +293,52 @@ func (gp *GP) Gradient() []float64 {
 	}
 	return grad
 }
+
+// OptResult reports what Optimize did (gogp_opt_result).
+type OptResult struct {
+	Iters, Evals int
+	LML0, LML    float64
+	Converged    bool
+}
+
+// Optimize runs the tutorial's MLE loop (tutorial/tutorial.go:124-175) inside
+// the library over gp.X, gp.Y: alg "adam" is the infer.Adam loop, "lbfgs" the
+// optimize.Minimize call; iters, threshold, rate are ITERS, THRESHOLD, RATE.  x
+// holds the log hyperparameters and is updated in place.  This form maximises
+// the marginal likelihood alone; priors (gp.Model) go through gogp_optimize's
+// callback argument with an exported cgo function -- see INTEGRATION.md.
+func (gp *GP) Optimize(x []float64, alg string, iters int, threshold, rate float64) (OptResult, error) {
+	gp.defaults()
+	h, err := gp.handle()
+	if err != nil {
+		return OptResult{}, err
+	}
+	if len(x) != gp.Simil.NTheta()+gp.ntn() {
+		return OptResult{}, errors.New("len(x)")
+	}
+	xf := flatten(gp.X, gp.NDim)
+	if st := C.gogp_set_data(h, dptr(xf), dptr(gp.Y), C.int64_t(len(gp.Y))); st != C.GOGP_OK {
+		return OptResult{}, gp.fail(st)
+	}
+	var s C.gogp_opt_settings
+	if alg == "lbfgs" {
+		s.method = 1
+	}
+	s.max_iters = C.int(iters)
+	s.threshold = C.double(threshold)
+	s.rate = C.double(rate)
+	var r C.gogp_opt_result
+	if st := C.gogp_optimize(h, &s, dptr(x), nil, nil, &r); st != C.GOGP_OK {
+		return OptResult{}, gp.fail(st)
+	}
+	gp.withObs, gp.n = false, len(gp.Y)
+	nts := gp.Simil.NTheta()
+	for i := range x {
+		if i < nts {
+			gp.ThetaSimil[i] = math.Exp(x[i])
+		} else {
+			gp.ThetaNoise[i-nts] = math.Exp(x[i])
+		}
+	}
+	return OptResult{int(r.iters), int(r.evals), float64(r.lml0), float64(r.lml), r.converged != 0}, nil
+}

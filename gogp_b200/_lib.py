@@ -24,11 +24,26 @@ PHASES = ("upload", "build", "potrf", "solve", "potri", "trace", "predict")
 # every symbol include/gogp_b200.h declares
 SYMBOLS = (
     "gogp_create", "gogp_destroy", "gogp_set_events", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_lml",
-    "gogp_produce", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
+    "gogp_produce", "gogp_optimize", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
     "gogp_debug_gemm", "gogp_debug_leaf", "gogp_debug_leaf_run", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
     "gogp_dev_gemm", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
 )
+
+
+class OptSettings(C.Structure):
+    """gogp_opt_settings"""
+    _fields_ = [("method", C.c_int), ("max_iters", C.c_int), ("threshold", C.c_double), ("rate", C.c_double),
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("history", C.c_int)]
+
+
+class OptResult(C.Structure):
+    """gogp_opt_result"""
+    _fields_ = [("iters", C.c_int), ("evals", C.c_int), ("lml0", C.c_double), ("lml", C.c_double),
+                ("converged", C.c_int)]
+
+
+PRIOR_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double))
 
 
 class Op(C.Structure):
@@ -75,6 +90,8 @@ def lib():
     L.gogp_lml.restype = C.c_int
     L.gogp_produce.argtypes = [H, dp, C.c_int64, dp, dp]
     L.gogp_produce.restype = C.c_int
+    L.gogp_optimize.argtypes = [H, C.POINTER(OptSettings), dp, PRIOR_FN, C.c_void_p, C.POINTER(OptResult)]
+    L.gogp_optimize.restype = C.c_int
     L.gogp_get_alpha.argtypes = [H, dp, C.c_int64]
     L.gogp_get_alpha.restype = C.c_int
     L.gogp_get_factor.argtypes = [H, dp, C.c_int64]

@@ -12,6 +12,7 @@
 #include "../../include/gogp_b200.h"
 #include "blocked.hpp"
 #include "kernels.h"
+#include "optimize.hpp"
 #include "program.h"
 
 using namespace gogp;
@@ -753,6 +754,50 @@ gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu,
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
     h->phase_ms[GOGP_PHASE_PREDICT] = ms;
+    return GOGP_OK;
+}
+
+gogp_status gogp_optimize(gogp_handle* h, const gogp_opt_settings* st, double* log_theta, gogp_prior_fn prior,
+                          void* ctx, gogp_opt_result* result) {
+    if (!h || !st || !result) return GOGP_BAD_ARGUMENT;
+    const int P = h->nts + h->ntn;
+    if (!log_theta && P > 0) return fail(h, GOGP_BAD_ARGUMENT, "log_theta is NULL");
+    if (st->method != 0 && st->method != 1) return fail(h, GOGP_BAD_ARGUMENT, "method must be 0 (adam) or 1 (lbfgs)");
+    if (st->max_iters < 0) return fail(h, GOGP_BAD_ARGUMENT, "max_iters must not be negative");
+    if (!h->has_data) return fail(h, GOGP_NOT_READY, "gogp_optimize needs the data set by gogp_set_data");
+    OptSettings s;
+    s.method = st->method;
+    s.max_iters = st->max_iters;
+    s.threshold = st->threshold;
+    s.rate = st->rate > 0.0 ? st->rate : 0.01;
+    s.beta1 = st->beta1 > 0.0 ? st->beta1 : 0.9;
+    s.beta2 = st->beta2 > 0.0 ? st->beta2 : 0.999;
+    s.eps = st->eps > 0.0 ? st->eps : 1e-8;
+    s.history = st->history > 0 ? st->history : 15;
+    gogp_status hard = GOGP_OK;  // anything but "not positive definite" aborts the loop
+    auto eval = [&](const double* x, double* f, double* g) {
+        if (hard != GOGP_OK) return false;
+        double lml = 0.0;
+        gogp_status e = gogp_observe(h, x, 0, nullptr, nullptr, 0, &lml);
+        if (e == GOGP_OK) e = gogp_gradient(h, g, P);
+        if (e != GOGP_OK) {
+            if (e != GOGP_NOT_POSITIVE_DEFINITE) hard = e;
+            return false;
+        }
+        if (prior) lml += prior(ctx, x, P, g);
+        *f = lml;
+        return true;
+    };
+    std::vector<double> x(log_theta, log_theta + P);
+    const OptResult r = s.method == 0 ? adam_ascent(eval, x, s) : lbfgs_ascent(eval, x, s);
+    result->iters = r.iters;
+    result->evals = r.evals;
+    result->lml0 = r.f0;
+    result->lml = r.f;
+    result->converged = r.converged;
+    if (hard != GOGP_OK) return hard;  // h->err was set by the failing call
+    if (r.failed) return fail(h, GOGP_NOT_POSITIVE_DEFINITE, "gogp_optimize: the starting point cannot be evaluated");
+    for (int i = 0; i < P; ++i) log_theta[i] = x[i];
     return GOGP_OK;
 }
 

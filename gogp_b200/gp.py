@@ -215,6 +215,49 @@ class GP:
             raise GoGPPanic(st, self._err(st))
         return grad
 
+    # -- tutorial/tutorial.go:124-175, run inside the library ----
+    def Optimize(self, x, alg="lbfgs", iters=1000, threshold=1e-6, rate=0.01, priors=None, history=0):
+        """The tutorial's MLE loop over gp.X, gp.Y without leaving the library: ``alg`` is "lbfgs"
+        (optimize.Minimize, tutorial/tutorial.go:131-155) or "adam" (infer.Adam, :156-168); ``iters``,
+        ``threshold``, ``rate`` are ITERS, THRESHOLD, RATE.  ``priors`` is gp.Model's Priors (an object
+        with Observe(x) and Gradient()) or None.  x (log hyper-parameters, float64) is updated in
+        place; returns a dict with iters, evals, lml0, lml, converged."""
+        self._defaults()
+        h = self._handle()
+        L = _lib.lib()
+        P = self._nts() + self._ntn()
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous and len(x) == P):
+            raise TypeError("Optimize takes a contiguous float64 numpy array of the %d log hyper-parameters" % P)
+        X = _flat(self.X, self.NDim)
+        Y = _flat(self.Y, 0)
+        n = len(Y)
+        if X.size != n * self.NDim:
+            raise GoGPPanic(_lib.BAD_ARGUMENT, "len(gp.X) != len(gp.Y)")
+        st = L.gogp_set_data(h, _lib.dptr(X), _lib.dptr(Y), n)
+        if st != _lib.OK:
+            raise GoGPPanic(st, self._err(st))
+        settings = _lib.OptSettings(method={"adam": 0, "lbfgs": 1}[alg], max_iters=iters, threshold=threshold,
+                                    rate=rate, beta1=0.0, beta2=0.0, eps=0.0, history=history)
+        result = _lib.OptResult()
+
+        def _prior(ctx, xp, np_, gp_):
+            xs = np.ctypeslib.as_array(xp, shape=(np_,)).copy()
+            ll = float(priors.Observe(xs))
+            g = np.asarray(priors.Gradient(), dtype=np.float64)
+            ga = np.ctypeslib.as_array(gp_, shape=(np_,))
+            ga[:len(g)] += g
+            return ll
+
+        cb = _lib.PRIOR_FN(_prior) if priors is not None else C.cast(None, _lib.PRIOR_FN)
+        st = L.gogp_optimize(h, C.byref(settings), _lib.dptr(x), cb, None, C.byref(result))
+        if st != _lib.OK:
+            raise GoGPPanic(st, self._err(st))
+        self._with_obs, self._n = False, n
+        self.ThetaSimil = list(np.exp(x[:self._nts()]))
+        self.ThetaNoise = list(np.exp(x[self._nts():]))
+        return {"iters": result.iters, "evals": result.evals, "lml0": result.lml0, "lml": result.lml,
+                "converged": bool(result.converged)}
+
     # -- extras over the C-ABI ---------------------------------------------------------
     def PhaseTimes(self):
         ms = np.zeros(len(_lib.PHASES))

@@ -204,6 +204,35 @@ gogp_status gogp_dev_gemv_sub(gogp_handle* h, const double* B, int64_t ld, int64
 gogp_status gogp_dev_trsv(gogp_handle* h, const double* L, int64_t ld, const double* winv, double* rhs, double* z,
                           int64_t n, void* stream);
 
+/* ---- hyper-parameter optimisation without leaving the process ----
+ * The tutorial's MLE drivers (tutorial/tutorial.go:124-175) over the data set by gogp_set_data:
+ * method 0 = the infer.Adam loop (:156-168), method 1 = L-BFGS as optimize.Minimize is used
+ * (:131-155).  X and Y stay resident in HBM; per evaluation only the parameters go down and
+ * LML + gradient come back.  The objective is LML(log_theta) + prior(log_theta), maximised;
+ * `prior` may be NULL (plain MLE) or a host callback that returns the log prior at x and ADDS
+ * its gradient to grad (gp.Model's Priors, gp/model.go:17-27; in Go an exported cgo function).
+ * log_theta (ntheta_simil + ntheta_noise values) is updated in place.  A point where the
+ * covariance is not positive definite is a rejected step, not an error; GOGP_NOT_POSITIVE_DEFINITE
+ * is returned only if the starting point itself fails. */
+typedef struct {
+    int method;        /* 0 adam, 1 lbfgs */
+    int max_iters;     /* ITERS */
+    double threshold;  /* THRESHOLD: stop when every |gradient_i| is below it */
+    double rate;       /* Adam RATE */
+    double beta1, beta2, eps; /* Adam moments; 0 selects 0.9, 0.999, 1e-8 */
+    int history;       /* L-BFGS pairs kept; 0 selects 15 */
+} gogp_opt_settings;
+typedef struct {
+    int iters;         /* Adam steps / L-BFGS directions taken */
+    int evals;         /* LML + gradient evaluations spent */
+    double lml0;       /* objective at the starting point */
+    double lml;        /* objective at the returned point */
+    int converged;     /* 1: gradient threshold met */
+} gogp_opt_result;
+typedef double (*gogp_prior_fn)(void* ctx, const double* x, int64_t n, double* grad);
+gogp_status gogp_optimize(gogp_handle* h, const gogp_opt_settings* settings, double* log_theta,
+                          gogp_prior_fn prior, void* ctx, gogp_opt_result* result);
+
 /* Test/diagnostic access to device state: what = 0 K (before factorisation is
  * not kept; returns the factor buffer), 1 L, 2 K^-1 (after gogp_gradient).
  * out is N x N row-major, lower triangle valid, upper mirrored. */

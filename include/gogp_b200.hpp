@@ -217,6 +217,35 @@ public:
         return grad;
     }
 
+    // tutorial/tutorial.go:124-175 inside the library (gogp_optimize): alg 0 = the infer.Adam loop,
+    // 1 = L-BFGS; x (log hyper-parameters) is updated in place over gp.X, gp.Y.  prior may be null.
+    gogp_opt_result Optimize(std::vector<double>& x, int alg, int iters, double threshold, double rate = 0.01,
+                             gogp_prior_fn prior = nullptr, void* ctx = nullptr) {
+        defaults();
+        Error e = handle();
+        if (!e.ok()) throw Panic(e.status, e.message);
+        const size_t P = (size_t)Simil.NTheta() + (size_t)noiseNTheta();
+        if (x.size() != P) throw Panic(GOGP_BAD_ARGUMENT, "len(x)");
+        std::vector<double> xf = flatten(X);
+        gogp_status st = gogp_set_data(h_, xf.data(), Y.data(), (int64_t)Y.size());
+        if (st != GOGP_OK) throw Panic(st, gogp_last_error(h_));
+        gogp_opt_settings s{};
+        s.method = alg;
+        s.max_iters = iters;
+        s.threshold = threshold;
+        s.rate = rate;
+        gogp_opt_result r{};
+        st = gogp_optimize(h_, &s, x.data(), prior, ctx, &r);
+        if (st != GOGP_OK) throw Panic(st, gogp_last_error(h_));
+        withObs_ = false;
+        n_ = (int64_t)Y.size();
+        ThetaSimil.resize((size_t)Simil.NTheta());
+        ThetaNoise.resize((size_t)noiseNTheta());
+        for (size_t i = 0; i < P; ++i)
+            (i < ThetaSimil.size() ? ThetaSimil[i] : ThetaNoise[i - ThetaSimil.size()]) = std::exp(x[i]);
+        return r;
+    }
+
 private:
     gogp_handle* h_ = nullptr;
     bool withObs_ = false;

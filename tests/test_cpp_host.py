@@ -37,3 +37,15 @@ def test_cpp_mirror_reference_tables():
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all ok" in r.stdout
+
+
+def test_optimiser_loops_on_analytic_objectives():
+    """gogp_b200/csrc/optimize.hpp (Adam / L-BFGS drivers behind gogp_optimize) is host code
+    templated on the objective: unit-tested here on a quadratic, Rosenbrock and a domain wall."""
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "cpp_opt_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp_opt_test.cc")])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all ok" in r.stdout

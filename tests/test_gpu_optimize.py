@@ -1,0 +1,114 @@
+"""gogp_optimize: the tutorial's MLE loops run inside the library,
+checked against the same loops driven from the host and against the oracle's optimum."""
+import numpy as np
+import pytest
+import scipy.optimize as so
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+class _NormalPrior:
+    """log theta_i ~ Normal(m_i, s_i), like tutorial/hyperpriors/model/model.go:23-37."""
+
+    def __init__(self, m, s):
+        self.m, self.s = np.asarray(m, float), np.asarray(s, float)
+
+    def Observe(self, x):
+        self.x = np.array(x, dtype=np.float64)
+        z = (self.x - self.m) / self.s
+        return float(np.sum(-0.5 * z * z - np.log(self.s) - 0.5 * np.log(2 * np.pi)))
+
+    def Gradient(self):
+        return -(self.x - self.m) / self.s ** 2
+
+
+def _oracle_objective(og, prior=None):
+    def f(x):
+        v = og.observe(x.copy())
+        g = og.gradient()
+        if prior is not None:
+            v += prior.Observe(x)
+            g = g + prior.Gradient()
+        return -v, -g
+    return f
+
+
+def test_adam_in_library_equals_host_driven_adam():
+    from gogp_b200.restarts import adam_ascent
+    name, N = "barebones", 300
+    X, y, logt = cases.synth(name, N, seed=3)
+    dg = cases.make_device_gp(name)
+    dg.X, dg.Y = X, y
+
+    def evaluate(t):
+        return dg.Observe(t), dg.Gradient()
+
+    lml_host, theta_host = adam_ascent(evaluate, logt, iters=25, rate=0.01, threshold=1e-6)
+    x = logt.copy()
+    res = dg.Optimize(x, alg="adam", iters=25, threshold=1e-6, rate=0.01)
+    assert res["iters"] == 25 and res["evals"] == 26 and not res["converged"]
+    assert np.max(np.abs(x - theta_host)) < 1e-12
+    assert abs(res["lml"] - lml_host) <= 1e-9 * max(1.0, abs(lml_host))
+    assert res["lml"] > res["lml0"]
+    # the handle is left at the returned point: LML(), Gradient, Produce follow from it
+    assert dg.LML() == res["lml"]
+
+
+@pytest.mark.parametrize("name,N", [("c2_rbf", 400), ("barebones", 250)])
+def test_lbfgs_reaches_the_oracle_optimum(name, N):
+    X, y, logt = cases.synth(name, N, seed=5)
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    x = logt.copy()
+    res = dg.Optimize(x, alg="lbfgs", iters=200, threshold=1e-5)
+    assert res["converged"] and res["lml"] >= res["lml0"]
+    ref = so.minimize(_oracle_objective(og), logt.copy(), jac=True, method="L-BFGS-B",
+                      options={"gtol": 1e-8, "ftol": 1e-15, "maxiter": 500})
+    assert abs(res["lml"] + ref.fun) <= 1e-6 * max(1.0, abs(ref.fun))
+    assert np.max(np.abs(x - ref.x)) < 1e-3
+    # the oracle agrees that the returned point is stationary and has that value
+    v = og.observe(x.copy())
+    assert abs(v - res["lml"]) <= 1e-9 * max(abs(v), N)
+    assert np.max(np.abs(og.gradient())) < 1e-4
+
+
+def test_priors_callback_matches_gp_model():
+    """LML + log prior through the C callback == gp.Model.Observe/Gradient (gp/model.go:17-27)."""
+    from gogp_b200 import Model
+    name, N = "hyperpriors", 300
+    X, y, logt = cases.synth(name, N, seed=6)
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    prior = _NormalPrior(logt, np.full(len(logt), 0.5))
+    # zero iterations of Adam = one evaluation of the objective at x
+    x = logt + 0.05
+    x0 = x.copy()
+    res = dg.Optimize(x, alg="adam", iters=0, priors=prior)
+    m = Model(dg, prior)
+    assert np.array_equal(x, x0)
+    assert abs(res["lml"] - m.Observe(x0.copy())) <= 1e-12 * max(1.0, abs(res["lml"]))
+    res = dg.Optimize(x, alg="lbfgs", iters=100, threshold=1e-5, priors=prior)
+    assert res["converged"]
+    ref = so.minimize(_oracle_objective(og, prior), x0.copy(), jac=True, method="L-BFGS-B",
+                      options={"gtol": 1e-8, "ftol": 1e-15, "maxiter": 500})
+    assert abs(res["lml"] + ref.fun) <= 1e-6 * max(1.0, abs(ref.fun))
+
+
+def test_bad_start_is_reported():
+    import gogp_b200 as g
+    name, N = "normal_const", 50
+    X, y, logt = cases.synth(name, N, seed=7)
+    dg = cases.make_device_gp(name)
+    dg.X, dg.Y = np.zeros((N, 1)), y      # identical inputs, noise 0.1: still positive definite
+    x = logt.copy()
+    assert dg.Optimize(x, alg="adam", iters=2)["evals"] >= 1
+    with pytest.raises(TypeError):
+        dg.Optimize(np.zeros(5), alg="adam")
+    with pytest.raises(KeyError):
+        dg.Optimize(x, alg="newton")
