@@ -27,7 +27,7 @@ SYMBOLS = (
     "gogp_produce", "gogp_optimize", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
     "gogp_debug_gemm", "gogp_debug_leaf", "gogp_debug_leaf_run", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
-    "gogp_dev_gemm", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
+    "gogp_dev_gemm", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_dev_trtri_t", "gogp_dev_trace_block", "gogp_noise_eval", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
 )
 
 
@@ -121,6 +121,11 @@ def lib():
     L.gogp_dev_sumlogdiag.argtypes = [H, vp, i64, i64, vp, vp]
     L.gogp_dev_gemv_sub.argtypes = [H, vp, i64, i64, i64, vp, vp, vp, vp]
     L.gogp_dev_trsv.argtypes = [H, vp, i64, vp, vp, vp, i64, vp]
+    L.gogp_dev_trtri_t.argtypes = [H, vp, i64, i64, vp, vp, vp]
+    L.gogp_dev_trace_block.argtypes = [H, dp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
+    L.gogp_noise_eval.argtypes = [H, dp, dp, dp]
+    for f in (L.gogp_dev_trtri_t, L.gogp_dev_trace_block, L.gogp_noise_eval):
+        f.restype = C.c_int
     for f in (L.gogp_dev_set_inputs, L.gogp_dev_cov_block, L.gogp_dev_potrf, L.gogp_dev_trsm, L.gogp_dev_gemm,
               L.gogp_dev_sumlogdiag, L.gogp_dev_gemv_sub, L.gogp_dev_trsv):
         f.restype = C.c_int

@@ -1100,6 +1100,47 @@ gogp_status gogp_dev_trsv(gogp_handle* h, const double* L, int64_t ld, const dou
     return GOGP_OK;
 }
 
+gogp_status gogp_dev_trtri_t(gogp_handle* h, const double* L, int64_t ld, int64_t n, const double* winv, double* out,
+                             void* stream) {
+    if (!h || !L || !winv || !out || n <= 0 || n % TILE) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    CudaBackend be{pick_stream(h, stream), h->dInfo, &h->launches, &h->prof, nullptr, 0};
+    Blocked<CudaBackend> bl{be, const_cast<double*>(L), ld, const_cast<double*>(winv), rl_max(), cols_max()};
+    bl.trtri_t(out, 0, n);
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_trace_block(gogp_handle* h, const double* theta_simil, const double* alpha, const double* kinv,
+                                 int64_t ld, int64_t row0, int64_t rows, int64_t col0, int64_t cols, double* acc,
+                                 double* scratch, void* stream) {
+    if (!h || !alpha || !kinv || !acc || !scratch || rows <= 0 || cols <= 0 || rows % TILE || cols % TILE ||
+        row0 % TILE || col0 % TILE)
+        return GOGP_BAD_ARGUMENT;
+    if (!h->dXt || row0 + rows > h->Npad || col0 + cols > h->Npad)
+        return fail(h, GOGP_BAD_ARGUMENT, "block outside the inputs set by gogp_dev_set_inputs");
+    CK(cudaSetDevice(h->dev));
+    std::vector<double> ts(h->nts > 0 ? h->nts : 1, 0.0);
+    if (theta_simil)
+        for (int i = 0; i < h->nts; ++i) ts[i] = theta_simil[i];
+    DevProgram prog;
+    h->simil.bind(ts.data(), &prog);
+    launch_grad_trace_block(prog, h->dXt, h->Npad, alpha, kinv, ld, h->N, h->ndim, row0, (int)(rows / TILE), col0,
+                            (int)(cols / TILE), scratch, acc, pick_stream(h, stream));
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_noise_eval(gogp_handle* h, const double* theta_noise, double* variance, double* dlog) {
+    if (!h || !variance || (!dlog && h->ntn > 0) || (!theta_noise && h->ntn > 0)) return GOGP_BAD_ARGUMENT;
+    std::vector<double> tn(h->ntn > 0 ? h->ntn : 1, 0.0), dl(h->ntn > 0 ? h->ntn : 1, 0.0);
+    for (int i = 0; i < h->ntn; ++i) tn[i] = theta_noise[i];
+    *variance = h->noise.eval_scalar(tn.data(), dl.data());
+    for (int i = 0; i < h->ntn; ++i) dlog[i] = dl[i];
+    return GOGP_OK;
+}
+
 gogp_status gogp_timer_start(gogp_handle* h) {
     if (!h) return GOGP_BAD_ARGUMENT;
     CK(cudaSetDevice(h->dev));

@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
                                                          const double* __restrict__ alpha,
                                                          const double* __restrict__ kinv, int64_t ld,
                                                          const double* __restrict__ kdiag, int64_t N, int D,
-                                                         double* __restrict__ partial) {
+                                                         double* __restrict__ partial, int rect_cols,
+                                                         int64_t grow0, int64_t gcol0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* xr = reinterpret_cast<double*>(smem_raw);
     double* xc = xr + D * TILE;
@@ -174,16 +175,30 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
     double* ww = pw + GT_E * 256;                     // [GT_E][256] weights w_e * W_e
     double* acc = ww + GT_E * 256;                    // [ntheta + 1][256] per-thread accumulators
 
+    // whole matrix: lower tiles, diagonal tiles in kdiag.  Block of a distributed matrix
+    // (rect_cols > 0): every tile of a rows x cols block whose origin is element (grow0, gcol0)
+    // of the global matrix; kinv points at the block and holds its diagonal tiles too.
     int ti, tj;
-    lower_tile(blockIdx.x, ti, tj);
-    const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
+    if (rect_cols > 0) {
+        ti = blockIdx.x / rect_cols;
+        tj = blockIdx.x % rect_cols;
+    } else {
+        lower_tile(blockIdx.x, ti, tj);
+    }
+    const int64_t lrow0 = (int64_t)ti * TILE, lcol0 = (int64_t)tj * TILE;
+    const int64_t row0 = grow0 + lrow0, col0 = gcol0 + lcol0;
     const int tid = threadIdx.x;
     const int nslot = prog.ntheta;  // slot ntheta = trace of W
+    if (col0 > row0 + TILE - 1) {   // a tile above the diagonal (upper part of a diagonal block): nothing counts
+        if (tid <= nslot) partial[(int64_t)blockIdx.x * (nslot + 1) + tid] = 0.0;
+        return;
+    }
     for (int q = 0; q <= nslot; ++q) acc[q * 256 + tid] = 0.0;
     stage_tiles(xr, xc, bar, Xt, ldx, row0, Xt, ldx, col0, D);
 
-    const double* ktile = (ti == tj) ? kdiag + (int64_t)ti * TILE * TILE : kinv + row0 * ld + col0;
-    const int64_t kld = (ti == tj) ? TILE : ld;
+    const bool side_diag = kdiag != nullptr && ti == tj;
+    const double* ktile = side_diag ? kdiag + (int64_t)ti * TILE * TILE : kinv + lrow0 * ld + lcol0;
+    const int64_t kld = side_diag ? TILE : ld;
     const int c0 = 2 * (tid & 63);
     const int ir = tid >> 6;
     const int64_t gj = col0 + c0;
@@ -263,7 +278,7 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
 
 // Deterministic second stage: one CTA per slot, fixed summation order.
 __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restrict__ partial, int nblocks, int nslots,
-                                                          double* __restrict__ out) {
+                                                          double* __restrict__ out, int accumulate) {
     __shared__ double sh[256];
     const int q = blockIdx.x;
     double s = 0.0;
@@ -274,7 +289,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restri
         if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[q] = sh[0];
+    if (threadIdx.x == 0) out[q] = accumulate ? out[q] + sh[0] : sh[0];
 }
 
 void launch_grad_trace(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,
@@ -285,8 +300,21 @@ void launch_grad_trace(const DevProgram& prog, const double* Xt, const double* a
     size_t smem = (size_t)2 * D * TILE * sizeof(double) + 16 + (size_t)2 * GT_E * 256 * sizeof(double) +
                   (size_t)(prog.ntheta + 1) * 256 * sizeof(double);
     cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    grad_trace_kernel<<<ntiles, 256, smem, s>>>(prog, Xt, Npad, alpha, kinv, Npad, kdiag, N, D, partial);
-    grad_reduce_kernel<<<prog.ntheta + 1, 256, 0, s>>>(partial, ntiles, prog.ntheta + 1, out);
+    grad_trace_kernel<<<ntiles, 256, smem, s>>>(prog, Xt, Npad, alpha, kinv, Npad, kdiag, N, D, partial, 0, 0, 0);
+    grad_reduce_kernel<<<prog.ntheta + 1, 256, 0, s>>>(partial, ntiles, prog.ntheta + 1, out, 0);
+}
+
+void launch_grad_trace_block(const DevProgram& prog, const double* Xt, int64_t ldx, const double* alpha,
+                             const double* kinv, int64_t ld, int64_t N, int D, int64_t grow0, int rtiles,
+                             int64_t gcol0, int ctiles, double* partial, double* out, cudaStream_t s) {
+    const int ntiles = rtiles * ctiles;
+    if (ntiles <= 0) return;
+    size_t smem = (size_t)2 * D * TILE * sizeof(double) + 16 + (size_t)2 * GT_E * 256 * sizeof(double) +
+                  (size_t)(prog.ntheta + 1) * 256 * sizeof(double);
+    cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    grad_trace_kernel<<<ntiles, 256, smem, s>>>(prog, Xt, ldx, alpha, kinv, ld, nullptr, N, D, partial, ctiles, grow0,
+                                                gcol0);
+    grad_reduce_kernel<<<prog.ntheta + 1, 256, 0, s>>>(partial, ntiles, prog.ntheta + 1, out, 1);
 }
 
 // ---- input gradient (with_obs) ---------------------------------------------------

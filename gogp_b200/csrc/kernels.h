@@ -38,6 +38,13 @@ void launch_cov_self(const DevProgram& prog, const double* Zt, int64_t M, int64_
 void launch_grad_trace(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,
                        const double* kdiag, int64_t N, int64_t Npad, int D, double* partial, double* out,
                        cudaStream_t s);
+// The same trace over one rows x cols block of a distributed K^-1 (block-cyclic layout): kinv
+// points at the block (ld), whose origin is element (grow0, gcol0) of the global matrix; only
+// elements with global row >= global column count.  out[0..ntheta] is ACCUMULATED into.
+// partial: scratch of rtiles * ctiles * (ntheta+1) doubles.
+void launch_grad_trace_block(const DevProgram& prog, const double* Xt, int64_t ldx, const double* alpha,
+                             const double* kinv, int64_t ld, int64_t N, int D, int64_t grow0, int rtiles,
+                             int64_t gcol0, int ctiles, double* partial, double* out, cudaStream_t s);
 // Input gradient for Observe's with_obs layout (gp/gp.go:118-129, 488-493):
 //   gx[i*D+d] = sum_{j != i} W_ij d k(x_i, x_j)/d x_{i,d}
 void launch_grad_inputs(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,

@@ -41,6 +41,7 @@ class CudaBlocks:
         st = self.L.gogp_create(ndim, sd, len(sd), simil.NTheta(), nd, len(nd) if nd is not None else 0,
                                 noise.NTheta() if noise is not None else 0, device, C.byref(self.h))
         self._ck(st)
+        self._nts = simil.NTheta()
         self.info = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def _ck(self, st):
@@ -96,6 +97,27 @@ class CudaBlocks:
         self._ck(self.L.gogp_dev_trsv(self.h, self._p(Lb), Lb.stride(0), self._p(winv), rhs.data_ptr(),
                                       z.data_ptr(), Lb.shape[0], self._stream()))
 
+    def trtri_t(self, Lb, winv, out):
+        assert Lb.stride(0) == out.stride(0)
+        self._ck(self.L.gogp_dev_trtri_t(self.h, self._p(Lb), Lb.stride(0), Lb.shape[0], self._p(winv), self._p(out),
+                                         self._stream()))
+
+    def trace_block(self, theta_s, alpha, blk, row0, col0, acc, scratch):
+        ts = np.ascontiguousarray(theta_s, dtype=np.float64)
+        self._ck(self.L.gogp_dev_trace_block(self.h, self._lib.dptr(ts), alpha.data_ptr(), self._p(blk), blk.stride(0),
+                                             row0, blk.shape[0], col0, blk.shape[1], acc.data_ptr(),
+                                             scratch.data_ptr(), self._stream()))
+
+    def noise_eval(self, theta_n):
+        tn = np.ascontiguousarray(theta_n, dtype=np.float64)
+        var = self.C.c_double(0.0)
+        dlog = np.zeros(max(1, len(tn)))
+        self._ck(self.L.gogp_noise_eval(self.h, self._lib.dptr(tn), self.C.byref(var), self._lib.dptr(dlog)))
+        return var.value, dlog[:len(tn)]
+
+    def nsimil(self):
+        return self._nts
+
     # look-ahead plumbing: run a batch of launches on a side stream, ordered after the
     # current point of the main (current) stream; wait_side() orders the main stream after it
     def side(self, fn):
@@ -109,6 +131,12 @@ class CudaBlocks:
             fn()
             self._side_done = torch.cuda.Event()
             self._side_done.record(self._side)
+        return self._side_done
+
+    def wait_event(self, ev):
+        """order the main (current) stream after a batch returned by side()"""
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def wait_side(self):
         if getattr(self, "_side_done", None) is not None:
@@ -161,6 +189,10 @@ class BlockCyclicCholesky:
         self.logdet2 = backend.zeros(2)
         self.sumlog = backend.zeros(1)
         self.factored = False
+        self.V = None        # L^-T, upper block triangular, same local layout (invert)
+        self.z = None        # L^-1 y, replicated (solve_lml)
+        self.alpha = None    # K^-1 y, replicated (solve_alpha)
+        self.have_kinv = False
         import os
         self.diag_after_bulk = os.environ.get("GOGP_DIAG_AFTER_BULK", "1") == "1"
 
@@ -171,9 +203,21 @@ class BlockCyclicCholesky:
         i, j, NB = self.ri[I], self.ci[J], self.NB
         return self.local[i * NB:(i + 1) * NB, j * NB:(j + 1) * NB]
 
-    def _bcast(self, t, src):
+    def _bcast(self, t, src, group=None):
         if self.world > 1:
-            self.dist.broadcast(t, src=src)
+            self.dist.broadcast(t, src=src, group=group)
+
+    def _groups(self):
+        """process-row and process-column groups (every rank creates all of them, in the same order)"""
+        if self.world == 1 or hasattr(self, "_row_groups"):
+            return
+        Pr, Pc = self.Pr, self.Pc
+        self._row_groups = [self.dist.new_group([r * Pc + c for c in range(Pc)]) for r in range(Pr)]
+        self._col_groups = [self.dist.new_group([r * Pc + c for r in range(Pr)]) for c in range(Pc)]
+
+    def vblock(self, I, J):
+        i, j, NB = self.ri[I], self.ci[J], self.NB
+        return self.V[i * NB:(i + 1) * NB, j * NB:(j + 1) * NB]
 
     # ---- build: every rank evaluates its own blocks from the replicated inputs ----
     def build(self, theta_simil, theta_noise):
@@ -297,6 +341,7 @@ class BlockCyclicCholesky:
         scratch = be.zeros(NB)
         zk = be.zeros(NB)
         ss = be.zeros(1)
+        zfull = be.zeros(nb * NB)
         for k in range(nb):
             acc.zero_()
             if k % self.Pr == self.r:
@@ -315,5 +360,166 @@ class BlockCyclicCholesky:
             if k in self.ci:
                 j = self.ci[k]
                 zcols[j * NB:(j + 1) * NB].copy_(zk)
+            zfull[k * NB:(k + 1) * NB].copy_(zk)
+        self.z = zfull
         quad = float(ss.item())
         return -0.5 * self.N * math.log(2 * math.pi) - 0.5 * self.logdet() - 0.5 * quad
+
+    # ---- K^-1 and the gradient across the grid (gp/gp.go:418-499) --------
+    # Everything stays in the one GEMM form C = beta C + alpha A B^T, as on one GPU:
+    #   V = L^-T (upper):  V_cc = L_cc^-T,  V_ic = -(sum_{k=i}^{c-1} V_ik L_ck^T) L_cc^-T   (i < c)
+    #   alpha = V z,       z = L^-1 y from solve_lml
+    #   K^-1 = V V^T:      K^-1_ij = sum_{c >= i} V_ic V_jc^T                               (i >= j)
+    #   grad_q = sum over owned blocks of the fused trace kernel, then one all-reduce of P+1 doubles.
+    def invert(self):
+        """V = L^-T, one block column at a time.  Step c: block row c of L goes down the process
+        columns; the owner of V_ik forms V_ik L_ck^T (one GEMM per owned block row, K = its owned
+        k in [i, c)); the partial sums are reduced along process rows to process column c mod Pc,
+        which solves with L_cc."""
+        assert self.factored
+        NB, be, nb = self.NB, self.be, self.nb
+        self._groups()
+        if self.V is None:
+            self.V = be.zeros(*self.local.shape)
+        else:
+            self.V.zero_()
+        maxc, maxr = max(1, len(self.my_cols)), max(1, len(self.my_rows))
+        lrow = be.empty(NB * maxc * NB)
+        sbuf = be.empty(maxr * NB * NB)
+        colg = self._col_groups[self.c] if self.world > 1 else None
+        rowg = self._row_groups[self.r] if self.world > 1 else None
+        for c in range(nb):
+            oc, pcc = self.owner(c, c), c % self.Pc
+            if self.c == pcc:
+                if self.rank == oc:
+                    be.trtri_t(self.block(c, c), self.winv_diag[c], self.vblock(c, c))
+                    self.lkk.copy_(self.block(c, c))
+                    self.wkk.copy_(self.winv_diag[c])
+                if c > 0:
+                    self._bcast(self.lkk, oc, colg)
+                    self._bcast(self.wkk, oc, colg)
+            if c == 0:
+                continue
+            ncl = sum(1 for J in self.my_cols if J < c)   # my block columns k < c
+            mine = [I for I in self.my_rows if I < c]     # my block rows i < c
+            buf = lrow[:NB * ncl * NB].view(NB, ncl * NB)
+            if ncl:
+                src = (c % self.Pr) * self.Pc + self.c
+                if self.rank == src:
+                    i = self.ri[c]
+                    buf.copy_(self.local[i * NB:(i + 1) * NB, :ncl * NB])
+                self._bcast(buf, src, colg)
+            if not mine:
+                continue
+            S = sbuf[:len(mine) * NB * NB].view(len(mine) * NB, NB)
+            for n, I in enumerate(mine):
+                j0 = sum(1 for J in self.my_cols if J < I)
+                Sn = S[n * NB:(n + 1) * NB]
+                if ncl > j0:
+                    i = self.ri[I]
+                    be.gemm(Sn, self.V[i * NB:(i + 1) * NB, j0 * NB:ncl * NB], buf[:, j0 * NB:ncl * NB], -1.0, 0.0)
+                else:
+                    Sn.zero_()
+            dst = self.r * self.Pc + pcc
+            if self.world > 1 and self.Pc > 1:
+                self.dist.reduce(S, dst=dst, group=rowg)
+            if self.rank == dst:
+                be.trsm(S, self.lkk, self.wkk)
+                j = self.ci[c]
+                self.V[:len(mine) * NB, j * NB:(j + 1) * NB].copy_(S)
+
+    def solve_alpha(self):
+        """alpha = K^-1 y = V z (replicated): block-row GEMVs with the owned blocks, one all-reduce."""
+        assert self.V is not None and self.z is not None
+        NB, be, nb = self.NB, self.be, self.nb
+        zc = be.zeros(max(1, len(self.my_cols)) * NB)
+        for j, J in enumerate(self.my_cols):
+            zc[j * NB:(j + 1) * NB].copy_(self.z[J * NB:(J + 1) * NB])
+        acc = be.zeros(nb * NB)
+        scratch = be.zeros(NB)
+        for I in self.my_rows:
+            j0 = sum(1 for J in self.my_cols if J < I)
+            if j0 < len(self.my_cols):
+                i = self.ri[I]
+                be.gemv_sub(self.V[i * NB:(i + 1) * NB, j0 * NB:len(self.my_cols) * NB], zc[j0 * NB:],
+                            acc[I * NB:(I + 1) * NB], scratch)
+        if self.world > 1:
+            self.dist.all_reduce(acc)
+        acc.neg_()
+        self.alpha = acc
+        return acc
+
+    def kinv(self):
+        """K^-1 = V V^T into the local blocks (the factor is overwritten).  Step c: block column c of V
+        goes to every rank, organised by process row as in factor(); every rank adds
+        V_ic V_jc^T to its blocks (i, j), j <= i <= c -- one GEMM per owned block row, on the side
+        stream, while the next block column is being broadcast."""
+        assert self.V is not None
+        NB, be, nb = self.NB, self.be, self.nb
+        events = {}
+        for c in range(nb):
+            panel, pc_buf = self.panels[c % 2], self.pc_bufs[c % 2]
+            be.wait_event(events.pop(c - 2, None))   # step c-2 read the buffers about to be overwritten
+            kc = c % self.Pc
+            for rr in range(self.Pr):
+                nrows = sum(1 for I in self.rows_of[rr] if I <= c)
+                if not nrows:
+                    continue
+                src = rr * self.Pc + kc
+                buf = panel[rr][:nrows]
+                if self.rank == src:
+                    j = self.ci[c]
+                    buf.copy_(self.V[:nrows * NB, j * NB:(j + 1) * NB].reshape(nrows, NB, NB))
+                self._bcast(buf, src)
+            mine = [I for I in self.my_rows if I <= c]
+            cols = [J for J in self.my_cols if J <= c]
+            if not mine or not cols:
+                continue
+            for n, J in enumerate(cols):
+                rr = J % self.Pr
+                pc_buf[n].copy_(panel[rr][self.rows_of[rr].index(J)])
+            pcm = pc_buf.reshape(-1, NB)
+
+            def bulk(c=c, mine=mine, cols=cols, panel=panel, pcm=pcm):
+                for I in mine:
+                    ncols = sum(1 for J in cols if J <= I)
+                    if not ncols:
+                        continue
+                    i = self.ri[I]
+                    A = panel[self.r][self.rows_of[self.r].index(I)]
+                    be.gemm(self.local[i * NB:(i + 1) * NB, :ncols * NB], A, pcm[:ncols * NB], 1.0,
+                            0.0 if c == I else 1.0)
+
+            events[c] = be.side(bulk)
+        be.wait_side()
+        self.factored = False
+        self.have_kinv = True
+
+    def gradient(self, theta_simil, theta_noise):
+        """d LML / d log theta (gp/gp.go:434-486): the fused trace over every owned block of
+        W = alpha alpha^T - K^-1, one all-reduce of ntheta_simil + 1 doubles; the noise parameters
+        follow from tr(W) on the host (all shipped noises are input-independent)."""
+        assert self.have_kinv and self.alpha is not None
+        NB, be = self.NB, self.be
+        nts = be.nsimil()
+        acc = be.zeros(nts + 1)
+        scratch = be.zeros((NB // 128) ** 2 * (nts + 1))
+        for I in self.my_rows:
+            for J in self.my_cols:
+                if J <= I:
+                    be.trace_block(theta_simil, self.alpha, self.block(I, J), I * NB, J * NB, acc, scratch)
+        if self.world > 1:
+            self.dist.all_reduce(acc)
+        g = acc.cpu().numpy() if hasattr(acc, "cpu") else np.asarray(acc)
+        _, dlog = be.noise_eval(theta_noise)
+        return np.concatenate([g[:nts], 0.5 * g[nts] * np.asarray(dlog, dtype=np.float64)])
+
+    def lml_and_gradient(self, theta_simil, theta_noise, y):
+        """build + factor + solve + K^-1 + trace: one LML + gradient evaluation across the grid."""
+        self.build(theta_simil, theta_noise)
+        self.factor()
+        lml = self.solve_lml(y)
+        self.invert()
+        self.solve_alpha()
+        self.kinv()
+        return lml, self.gradient(theta_simil, theta_noise)

@@ -233,6 +233,22 @@ typedef double (*gogp_prior_fn)(void* ctx, const double* x, int64_t n, double* g
 gogp_status gogp_optimize(gogp_handle* h, const gogp_opt_settings* settings, double* log_theta,
                           gogp_prior_fn prior, void* ctx, gogp_opt_result* result);
 
+/* Pieces of the distributed K^-1 and gradient, same conventions:
+ * out (n x n, upper triangular, same ld as L) = L^-T for one factored diagonal block; */
+gogp_status gogp_dev_trtri_t(gogp_handle* h, const double* L, int64_t ld, int64_t n, const double* winv, double* out,
+                             void* stream);
+/* the fused gradient trace over one rows x cols block of K^-1 whose origin is element (row0, col0)
+ * of the global matrix (only elements with global row >= global column count; alpha is the full
+ * padded vector; inputs from gogp_dev_set_inputs).  acc[0 .. ntheta_simil] is accumulated into:
+ * the similarity parameters' 0.5 tr(W dK/dlog theta) sums and, last, tr(W) of the block.
+ * scratch: (rows/128)(cols/128)(ntheta_simil+1) doubles. */
+gogp_status gogp_dev_trace_block(gogp_handle* h, const double* theta_simil, const double* alpha, const double* kinv,
+                                 int64_t ld, int64_t row0, int64_t rows, int64_t col0, int64_t cols, double* acc,
+                                 double* scratch, void* stream);
+/* Host arithmetic on the (input-independent) noise program: variance and d variance / d log theta_n
+ * at natural-scale theta_noise; the noise gradient is 0.5 tr(W) dlog[q] (gp/gp.go:133-150). */
+gogp_status gogp_noise_eval(gogp_handle* h, const double* theta_noise, double* variance, double* dlog);
+
 /* Test/diagnostic access to device state: what = 0 K (before factorisation is
  * not kept; returns the factor buffer), 1 L, 2 K^-1 (after gogp_gradient).
  * out is N x N row-major, lower triangle valid, upper mirrored. */

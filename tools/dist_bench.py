@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--no-lookahead", action="store_true")
+    ap.add_argument("--grad", action="store_true", help="also K^-1 and the gradient (SURVEY.md section 8 f-2)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -89,8 +90,15 @@ def main():
         t_build, _ = timed(lambda: ch.build(th[:NDIM + 1], th[NDIM + 1:]))
         t_fac, _ = timed(lambda: ch.factor(lookahead=not a.no_lookahead))
         t_sol, lml = timed(lambda: ch.solve_lml(y))
-        res.append((t_build, t_fac, t_sol, lml, be.launches() - l0))
-    t_build, t_fac, t_sol, lml, launches = res[-1]
+        gr = None
+        if a.grad:
+            t_inv, _ = timed(ch.invert)
+            t_alpha, _ = timed(ch.solve_alpha)
+            t_kinv, _ = timed(ch.kinv)
+            t_trace, grad = timed(lambda: ch.gradient(th[:NDIM + 1], th[NDIM + 1:]))
+            gr = (t_inv, t_alpha, t_kinv, t_trace, grad)
+        res.append((t_build, t_fac, t_sol, lml, be.launches() - l0, gr))
+    t_build, t_fac, t_sol, lml, launches, gr = res[-1]
     bad = be.bad_pivot()
     out = {
         "workload": "configs[4]: synthetic 4-D Matern32 + noise, block-cyclic Cholesky", "N": a.n, "NB": a.nb,
@@ -100,12 +108,25 @@ def main():
         "lml": lml, "bad_pivot": bad, "launches_rank0": launches,
         "mem_gb_rank0": torch.cuda.max_memory_allocated() / 1e9,
     }
+    if gr is not None:
+        t_inv, t_alpha, t_kinv, t_trace, grad = gr
+        total = t_build + t_fac + t_sol + t_inv + t_alpha + t_kinv + t_trace
+        out.update({"invert_ms": t_inv, "alpha_ms": t_alpha, "kinv_ms": t_kinv, "trace_ms": t_trace,
+                    "potri_tflops_total": 2 * a.n ** 3 / 3 / ((t_inv + t_kinv) * 1e-3) / 1e12,
+                    "eval_ms": total, "evals_per_s": 1e3 / total,
+                    "eval_tflops_total": a.n ** 3 / (total * 1e-3) / 1e12, "grad": [float(v) for v in grad]})
     if a.check and rank == 0:
+        del ch
+        torch.cuda.empty_cache()
         g = GP(NDim=NDIM, Simil=simil, Noise=noise, Device=local)
         g.X, g.Y = X, y
         ref = g.Observe(logt.copy())
         out["single_gpu_lml"] = ref
         out["rel_diff"] = abs(lml - ref) / max(abs(ref), a.n)
+        if gr is not None:
+            gref = g.Gradient()
+            out["single_gpu_grad"] = [float(v) for v in gref]
+            out["grad_rel_diff"] = float(np.max(np.abs(np.asarray(gr[4]) - gref)) / max(1.0, np.max(np.abs(gref))))
         g.close()
     if rank == 0:
         print(json.dumps(out), flush=True)
