@@ -33,27 +33,45 @@ def adam_ascent(evaluate, theta0, iters, rate=0.01, beta1=0.9, beta2=0.999, eps=
     return lml, theta
 
 
-def multi_start(evaluate, starts, rank=0, world=1, iters=0, dist=None):
-    """Run this rank's share of `starts` (R x P array, identical on every rank) and
-    gather all results.  Returns (lmls[R], thetas[R, P], best index); every rank
-    gets the same answer.  `dist` is torch.distributed (any backend) or None."""
+def run_share(evaluate, starts, rank=0, world=1, iters=0, optimise=None):
+    """This rank's share of `starts` (R x P array, identical on every rank): returns
+    (lmls[R], thetas[R, P]) with -inf / the start itself in the rows other ranks own.
+    `optimise`, if given, is start -> (objective, theta) and replaces the host-driven Adam
+    loop -- on the product path gp.GP.Optimize, i.e. the loop inside the library."""
     starts = np.asarray(starts, dtype=np.float64)
     R, P = starts.shape
     lmls = np.full(R, -np.inf)
     thetas = np.array(starts, copy=True)
     for r in shard(R, rank, world):
-        if iters > 0:
+        if optimise is not None:
+            lmls[r], thetas[r] = optimise(starts[r].copy())
+        elif iters > 0:
             lmls[r], thetas[r] = adam_ascent(evaluate, starts[r], iters)
         else:
             lmls[r], _ = evaluate(starts[r].copy())
+    return lmls, thetas
+
+
+def gather_results(lmls, thetas, rank=0, world=1, dist=None):
+    """The only exchange of the sharded restarts: every rank receives every restart's
+    (objective, theta), R*(P+1) doubles per rank.  Returns (lmls, thetas, best index)."""
+    R = len(lmls)
     if world > 1:
         import torch
         mine = torch.from_numpy(np.concatenate([lmls[:, None], thetas], axis=1))
         parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine)  # R*(P+1) doubles per rank: the only exchange
+        dist.all_gather(parts, mine)
         for w, part in enumerate(parts):
             idx = shard(R, w, world)
             a = part.numpy()
             lmls[idx] = a[idx, 0]
             thetas[idx] = a[idx, 1:]
     return lmls, thetas, int(np.argmax(lmls))
+
+
+def multi_start(evaluate, starts, rank=0, world=1, iters=0, dist=None, optimise=None):
+    """Run this rank's share of `starts` and gather all results.  Returns (lmls[R],
+    thetas[R, P], best index); every rank gets the same answer.  `dist` is torch.distributed
+    (any backend) or None."""
+    lmls, thetas = run_share(evaluate, starts, rank, world, iters, optimise)
+    return gather_results(lmls, thetas, rank, world, dist)

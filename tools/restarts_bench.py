@@ -1,0 +1,134 @@
+"""BASELINE configs[3]: the hyperpriors model (tutorial/hyperpriors), N = 16384, 64 multi-start
+restarts sharded across the GPUs of one box -- independent units, no data-path collective, one
+host-side gather of (objective, theta) per restart at the end.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 \
+      --master-port 29512 tools/restarts_bench.py [--size 16384] [--restarts 64] [--alg adam] [--iters 5]
+
+Every restart is the tutorial's MLE loop run INSIDE the library (gogp_optimize) on the rank's own
+handle, with the tutorial's priors through the C callback.  Prints one JSON line from rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gogp_b200 import GP, kernel as k, restarts  # noqa: E402
+
+
+class HyperPriors:
+    """tutorial/hyperpriors/model/model.go:10-40 restated: Normal log-densities on the log
+    hyper-parameters (c1, c2, l1, l2, p, s); c2's mean depends on c1."""
+
+    @staticmethod
+    def _logp(mu, sigma, x):
+        z = (x - mu) / sigma
+        return -0.5 * z * z - math.log(sigma) - 0.5 * math.log(2 * math.pi)
+
+    def Observe(self, x):
+        self.x = np.array(x, dtype=np.float64)
+        c1, c2, l1, l2, p, s = self.x
+        return (self._logp(-1, 1, c1) + self._logp(c1 - math.log(2), 1, c2) + self._logp(0, 2, l1) +
+                self._logp(0, 2, l2) + self._logp(0, 1, p) + self._logp(0, 1, s))
+
+    def Gradient(self):
+        c1, c2, l1, l2, p, s = self.x
+        d2 = c2 - (c1 - math.log(2))
+        return np.array([-(c1 + 1) + d2, -d2, -l1 / 4, -l2 / 4, -p, -s])
+
+    def sample(self, rng):
+        c1 = -1 + rng.standard_normal()
+        return np.array([c1, c1 - math.log(2) + rng.standard_normal(), 2 * rng.standard_normal(),
+                         2 * rng.standard_normal(), rng.standard_normal(), rng.standard_normal()])
+
+
+def synth(N, seed=0):
+    """x = 0.39269908 i (the spacing of tutorial/data/hyperpriors.csv),
+    y = trend + season (period 8) + 0.1 noise, normalised."""
+    rng = np.random.default_rng(seed)
+    x = 0.39269908 * np.arange(N)
+    y = 0.002 * x + np.sin(2 * np.pi * x / 8.0) + 0.1 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    return x[:, None], y
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", dest="n", type=int, default=16384)
+    ap.add_argument("--restarts", type=int, default=64)
+    ap.add_argument("--alg", default="adam", choices=["adam", "lbfgs"])
+    ap.add_argument("--iters", type=int, default=5)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("gloo")  # the only exchange is a host-side gather of R x (P+1) doubles
+    X, y = synth(a.n)
+    simil = k.Param(0) * k.Matern52.Of(l=2) + k.Param(1) * k.Periodic.Of(l=3, p=(4, 10.0))
+    g = GP(NDim=1, Simil=simil, Noise=0.01 * k.UniformNoise, Device=local)
+    g.X, g.Y = X, y
+    priors = HyperPriors()
+    rng = np.random.default_rng(7)
+    starts = np.stack([priors.sample(rng) for _ in range(a.restarts)])
+    starts[:, 2:4] = np.clip(starts[:, 2:4], -1.5, 1.5)   # keep the sampled length scales where K stays well conditioned
+    evals = [0]
+
+    def optimise(x0):
+        x = np.ascontiguousarray(x0, dtype=np.float64)
+        try:
+            res = g.Optimize(x, alg=a.alg, iters=a.iters, threshold=1e-4, rate=0.05, priors=priors)
+        except Exception:  # a start where K is not positive definite: the restart is dropped
+            return -np.inf, x0
+        evals[0] += res["evals"]
+        return res["lml"], x
+
+    optimise(starts[0].copy())  # warm-up (allocations); not counted
+    evals[0] = 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    import ctypes as C
+    from gogp_b200 import _lib
+    L, h, ms = _lib.lib(), g._handle(), C.c_double()
+    L.gogp_timer_start(h)       # CUDA events on the handle's stream bracket this rank's share
+    t0 = time.perf_counter()
+    obj, thetas = restarts.run_share(None, starts, rank, world, optimise=optimise)
+    L.gogp_timer_stop(h, C.byref(ms))
+    wall = time.perf_counter() - t0
+    dt = ms.value * 1e-3
+    obj, thetas, best = restarts.gather_results(obj, thetas, rank, world, dist if world > 1 else None)
+    tt = torch.tensor([dt, float(evals[0]), wall], dtype=torch.float64)
+    if world > 1:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        dt, total_evals, wall = float(tmax[0]), float(tt[1]), float(tmax[2])
+    else:
+        total_evals = float(tt[1])
+    if rank == 0:
+        print(json.dumps({
+            "workload": "configs[3]: hyperpriors model, multi-start restarts sharded across GPUs (no collective)",
+            "N": a.n, "restarts": a.restarts, "n_gpus": world, "alg": a.alg, "iters": a.iters,
+            "seconds": dt, "timing": "device time of each rank's share (CUDA events on its handle's stream), max over ranks",
+            "wall_seconds": wall, "restarts_per_s": a.restarts / dt, "evaluations": total_evals,
+            "evals_per_s_total": total_evals / dt, "best_restart": best, "best_objective": float(obj[best]),
+            "best_theta": [float(v) for v in np.exp(thetas[best])],
+            "finite_restarts": int(np.sum(np.isfinite(obj))),
+        }), flush=True)
+    g.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
