@@ -224,6 +224,8 @@ struct gogp_handle {
     double *dB = nullptr, *dDg = nullptr, *dPartial = nullptr;
     double *dAlpha = nullptr, *dW = nullptr, *dZ = nullptr, *dRed = nullptr, *dGx = nullptr;
     int* dInfo = nullptr;
+    unsigned* dSync = nullptr;  // ticket + ready flags of the single-launch triangular solves
+    int64_t syncCap = 0;
     double* dScr = nullptr;  // [scrRows][128] scratch of the out-of-place block solves
     int64_t scrRows = 0;
     double* hPin = nullptr;  // pinned staging for small results
@@ -311,6 +313,13 @@ gogp_status ensure_capacity(gogp_handle* h, int64_t Npad) {
     CK(cudaMalloc(&h->dW, v));
     CK(cudaMalloc(&h->dZ, v));
     CK(cudaMalloc(&h->dGx, v * h->ndim));
+    if (Npad / TILE + 1 > h->syncCap) {
+        if (h->dSync) cudaFree(h->dSync);
+        h->dSync = nullptr;
+        h->syncCap = 0;
+        CK(cudaMalloc(&h->dSync, (size_t)(Npad / TILE + 1) * sizeof(unsigned)));
+        h->syncCap = Npad / TILE + 1;
+    }
     h->cap = Npad;
     return GOGP_OK;
 }
@@ -408,8 +417,8 @@ gogp_status absorb(gogp_handle* h) {
 
     // alpha = L^-T (L^-1 y)
     CK(cudaMemcpyAsync(h->dW, h->dY, (size_t)Npad * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    launch_trsv_lower(h->dA, Npad, h->dWinv, h->dW, h->dZ, Npad, false, s, &h->launches);
-    launch_trsv_lower(h->dA, Npad, h->dWinv, h->dZ, h->dAlpha, Npad, true, s, &h->launches);
+    launch_trsv_lower(h->dA, Npad, h->dWinv, h->dW, h->dZ, Npad, false, s, &h->launches, h->dSync);
+    launch_trsv_lower(h->dA, Npad, h->dWinv, h->dZ, h->dAlpha, Npad, true, s, &h->launches, h->dSync);
     launch_logdet_dot(h->dA, Npad, h->dY, h->dAlpha, N, h->dRed, s);
     ++h->launches;
     CK(cudaEventRecord(h->ev[3], s));
@@ -509,6 +518,7 @@ void gogp_destroy(gogp_handle* h) {
     free_dev(h->dB); free_dev(h->dDg); free_dev(h->dPartial); free_dev(h->dRed);
     free_dev(h->dZraw); free_dev(h->dZt); free_dev(h->dBt); free_dev(h->dPv); free_dev(h->dScr);
     if (h->dInfo) cudaFree(h->dInfo);
+    if (h->dSync) cudaFree(h->dSync);
     if (h->hPin) cudaFreeHost(h->hPin);
     for (auto& ev : h->ev)
         if (ev) cudaEventDestroy(ev);
@@ -1095,7 +1105,8 @@ gogp_status gogp_dev_trsv(gogp_handle* h, const double* L, int64_t ld, const dou
                           int64_t n, void* stream) {
     if (!h || !L || !winv || !rhs || !z || n <= 0 || n % TILE) return GOGP_BAD_ARGUMENT;
     CK(cudaSetDevice(h->dev));
-    launch_trsv_lower(L, ld, winv, rhs, z, n, false, pick_stream(h, stream), &h->launches);
+    // the block-cyclic path solves one diagonal block at a time on the caller's stream: step kernels
+    launch_trsv_lower(L, ld, winv, rhs, z, n, false, pick_stream(h, stream), &h->launches, nullptr);
     CK(cudaGetLastError());
     return GOGP_OK;
 }

@@ -79,9 +79,10 @@ void set_leaf_variant(int v);  // timing aid, see leaf.cu
 // dst tile (ld) = winv^T (upper triangular, strictly-lower zeroed).
 void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t s);
 // Blocked triangular solves with the tile inverses.  fwd: out = L^-1 rhs; bwd: out = L^-T rhs.
-// rhs (Npad) is destroyed; out must not alias it.
+// rhs (Npad) may be destroyed; out must not alias it.  sync: Npad/128 + 1 unsigned ints of device
+// scratch for the single-launch kernels (NULL: one launch per block).
 void launch_trsv_lower(const double* L, int64_t ld, const double* winv, double* rhs, double* out, int64_t Npad,
-                       bool transposed, cudaStream_t s, int64_t* launches);
+                       bool transposed, cudaStream_t s, int64_t* launches, unsigned* sync);
 // dst[r][c] = src[r][c] for a rows x cols block (cols even, 16-byte aligned rows)
 void launch_copy_block(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols,
                        cudaStream_t s);

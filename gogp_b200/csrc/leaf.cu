@@ -458,6 +458,178 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __rest
     if (!half) x[J * TILE + c] = s + part[c];
 }
 
+// ---- single-launch triangular solves (default) --------------------------------------------
+// The step kernels above cost one launch per 128-row block (2 x 255 dependent launches at
+// N = 32768, ~21 us each).  Here ONE launch per direction: a CTA per 128-row block takes a
+// ticket (so blocks start in dependency order whatever the hardware's dispatch order), streams
+// its row (forward) / column (backward) of L block by block, and for each block waits on a
+// ready flag that the producing CTA releases after storing its part of the solution
+// (st.release.gpu after __threadfence / ld.acquire.gpu).  A CTA only ever waits for smaller
+// tickets, which are running or finished, so there is no deadlock however many CTAs are
+// resident.  The block of L is prefetched into registers BEFORE the wait and the 128x128
+// inverse of the CTA's own diagonal tile sits in shared memory, so the dependent chain per
+// block is: flag -> 1 KB of the solution from L2 -> FMAs -> one reduction -> tile matvec -> release.
+// sync[0] is the ticket counter, sync[1 + b] the flag of block b; zeroed by the launcher.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_flag(const unsigned* p, int lane) {
+    if (lane == 0)
+        while (ld_acquire_u32(p) == 0) {
+        }
+    __syncwarp();
+    (void)ld_acquire_u32(p);  // every lane acquires once the flag is known to be set
+}
+
+constexpr int WP = 130;  // smem pitch of the staged tile inverse
+
+__device__ __forceinline__ void stage_winv(double* Ws, const double* __restrict__ W, int tid) {
+    for (int idx = tid; idx < TILE * (TILE / 2); idx += 256) {
+        const int r = idx >> 6, c2 = (idx & 63) * 2;
+        *reinterpret_cast<double2*>(Ws + r * WP + c2) = *reinterpret_cast<const double2*>(W + r * TILE + c2);
+    }
+}
+
+// z = L^-1 rhs.  Warp w owns rows 16w .. 16w+15 of the CTA's block row, lane l the columns
+// 4l .. 4l+3 of every block: partial dot products stay per lane until the row is complete.
+__global__ void __launch_bounds__(256, 1) trsv_fwd_chain_kernel(const double* __restrict__ L, int64_t ld,
+                                                                const double* __restrict__ winv,
+                                                                const double* __restrict__ rhs, double* z, int T,
+                                                                unsigned* sync) {
+    extern __shared__ __align__(16) double Ws[];  // [128][WP]
+    __shared__ double ws[TILE];
+    __shared__ int s_i;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_i = (int)atomicAdd(&sync[0], 1u);
+    __syncthreads();
+    const int i = s_i;
+    stage_winv(Ws, winv + (int64_t)i * TILE * TILE, tid);
+    const double* Lrow = L + ((int64_t)i * TILE + warp * 16) * ld + 4 * lane;
+    double acc[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) acc[rr] = 0.0;
+    for (int J = 0; J < i; ++J) {
+        double2 a0[16], a1[16];
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            const double2* p = reinterpret_cast<const double2*>(Lrow + (int64_t)rr * ld + (int64_t)J * TILE);
+            a0[rr] = p[0];
+            a1[rr] = p[1];
+        }
+        wait_flag(sync + 1 + J, lane);
+        const double2 z0 = __ldcg(reinterpret_cast<const double2*>(z + (int64_t)J * TILE + 4 * lane));
+        const double2 z1 = __ldcg(reinterpret_cast<const double2*>(z + (int64_t)J * TILE + 4 * lane + 2));
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr)
+            acc[rr] += a0[rr].x * z0.x + a0[rr].y * z0.y + a1[rr].x * z1.x + a1[rr].y * z1.y;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[rr] += __shfl_xor_sync(0xffffffffu, acc[rr], o);
+    if (lane < 16) ws[warp * 16 + lane] = rhs[(int64_t)i * TILE + warp * 16 + lane] - pick(acc, lane);
+    __syncthreads();  // ws complete, tile inverse staged
+    {
+        const double v0 = ws[4 * lane], v1 = ws[4 * lane + 1], v2 = ws[4 * lane + 2], v3 = ws[4 * lane + 3];
+        double out[16];
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            const double* wr = Ws + (warp * 16 + rr) * WP + 4 * lane;
+            out[rr] = wr[0] * v0 + wr[1] * v1 + wr[2] * v2 + wr[3] * v3;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) out[rr] += __shfl_xor_sync(0xffffffffu, out[rr], o);
+        if (lane < 16) z[(int64_t)i * TILE + warp * 16 + lane] = pick(out, lane);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        st_release_u32(sync + 1 + i, 1u);
+    }
+}
+
+// x = L^-T zin.  Same tiling of each block L[I, J] (warp: 16 rows, lane: 4 columns), but the sums
+// run over rows, so every lane keeps its 4 column sums and the warps meet once at the end.
+__global__ void __launch_bounds__(256, 1) trsv_bwd_chain_kernel(const double* __restrict__ L, int64_t ld,
+                                                                const double* __restrict__ winv,
+                                                                const double* __restrict__ zin, double* x, int T,
+                                                                unsigned* sync) {
+    extern __shared__ __align__(16) double Ws[];  // [128][WP]
+    __shared__ double ws[TILE];
+    __shared__ double part[8][TILE];
+    __shared__ int s_i;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_i = (int)atomicAdd(&sync[0], 1u);
+    __syncthreads();
+    const int J = T - 1 - s_i;
+    stage_winv(Ws, winv + (int64_t)J * TILE * TILE, tid);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int I = T - 1; I > J; --I) {
+        const double* Lblk = L + ((int64_t)I * TILE + warp * 16) * ld + (int64_t)J * TILE + 4 * lane;
+        double2 a0[16], a1[16];
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            const double2* p = reinterpret_cast<const double2*>(Lblk + (int64_t)rr * ld);
+            a0[rr] = p[0];
+            a1[rr] = p[1];
+        }
+        wait_flag(sync + 1 + I, lane);
+        const double* xr = x + (int64_t)I * TILE + warp * 16;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr += 2) {
+            const double2 xv = __ldcg(reinterpret_cast<const double2*>(xr + rr));
+            acc[0] += a0[rr].x * xv.x + a0[rr + 1].x * xv.y;
+            acc[1] += a0[rr].y * xv.x + a0[rr + 1].y * xv.y;
+            acc[2] += a1[rr].x * xv.x + a1[rr + 1].x * xv.y;
+            acc[3] += a1[rr].y * xv.x + a1[rr + 1].y * xv.y;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[warp][4 * lane + q] = acc[q];
+    __syncthreads();
+    if (tid < TILE) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += part[w][tid];
+        ws[tid] = zin[(int64_t)J * TILE + tid] - sum;
+    }
+    __syncthreads();
+    {
+        double o4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            const double* wr = Ws + (warp * 16 + rr) * WP + 4 * lane;
+            const double v = ws[warp * 16 + rr];
+            o4[0] += wr[0] * v;
+            o4[1] += wr[1] * v;
+            o4[2] += wr[2] * v;
+            o4[3] += wr[3] * v;
+        }
+        __syncthreads();  // part[] is reused
+#pragma unroll
+        for (int q = 0; q < 4; ++q) part[warp][4 * lane + q] = o4[q];
+    }
+    __syncthreads();
+    if (tid < TILE) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += part[w][tid];
+        x[(int64_t)J * TILE + tid] = sum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        st_release_u32(sync + 1 + J, 1u);
+    }
+}
+
 __global__ void __launch_bounds__(1024) logdet_dot_kernel(const double* __restrict__ L, int64_t ld,
                                                           const double* __restrict__ y,
                                                           const double* __restrict__ alpha, int64_t N,
@@ -592,10 +764,32 @@ void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t
 }
 
 void launch_trsv_lower(const double* L, int64_t ld, const double* winv, double* rhs, double* out, int64_t Npad,
-                       bool transposed, cudaStream_t s, int64_t* launches) {
-    // rhs is consumed (it is the running right-hand side); out must not alias it:
-    // CTA 0 of a step stores block I of the result while the others still read rhs_I.
+                       bool transposed, cudaStream_t s, int64_t* launches, unsigned* sync) {
+    // rhs may be consumed (the step kernels use it as the running right-hand side); out must not alias it.
     const int T = (int)(Npad / TILE);
+    static int chain = -1;  // 1: one launch per direction (default), 0: one launch per block (GOGP_TRSV=0)
+    if (chain < 0) {
+        const char* e = getenv("GOGP_TRSV");
+        chain = e ? atoi(e) : 1;
+    }
+    if (chain && sync && T > 1) {
+        const size_t smem = (size_t)TILE * WP * sizeof(double);
+        static bool configured[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
+            cudaFuncSetAttribute(trsv_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(trsv_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured[dev & 63] = true;
+        }
+        cudaMemsetAsync(sync, 0, (size_t)(T + 1) * sizeof(unsigned), s);
+        if (!transposed)
+            trsv_fwd_chain_kernel<<<T, 256, smem, s>>>(L, ld, winv, rhs, out, T, sync);
+        else
+            trsv_bwd_chain_kernel<<<T, 256, smem, s>>>(L, ld, winv, rhs, out, T, sync);
+        if (launches) *launches += 1;
+        return;
+    }
     if (!transposed) {
         trsv_first_kernel<<<1, 256, 0, s>>>(winv, rhs, out, 0, 0);
         for (int I = 0; I + 1 < T; ++I) trsv_fwd_step_kernel<<<T - 1 - I, 256, 0, s>>>(L, ld, winv, rhs, out, I);
