@@ -14,8 +14,8 @@ namespace gogp {
 #define GOGP_SQRT5 2.2360679774997900
 #define GOGP_PI 3.14159265358979323846
 
-// Length-scale divisions use the host-computed reciprocal i0 = 1/(scale*theta)
-// (d differs from the reference's r/l by at most one ulp).
+// Length-scale and period divisions use the host-computed reciprocals i0 = 1/(scale*theta),
+// i1 = pi/(scale*theta_p) (d differs from the reference's r/l by at most an ulp or two).
 // tutorial/events/kernel/kernel.go:33-44: order the pair, the first event whose from- or to-boundary
 // lies in (lo, hi] discounts the similarity.
 __device__ __forceinline__ double events_value(const DevProgram& prog, double xa, double xb) {
@@ -36,7 +36,7 @@ __device__ __forceinline__ double factor_value(const DevFactor& f, double xa, do
             return exp(-d * d / 2);
         }
         case F_PERIODIC: {
-            double d = sin(GOGP_PI * fabs(xa - xb) / f.a1) / f.a0;
+            double d = sin(fabs(xa - xb) * f.i1) * f.i0;
             return exp(-2 * d * d);
         }
         case F_MATERN32: {
@@ -90,12 +90,12 @@ __device__ __forceinline__ void factor_dlog_theta(const DevFactor& f, double xa,
             return;
         }
         case F_PERIODIC: {
-            double u = GOGP_PI * fabs(xa - xb) / f.a1;
+            double u = fabs(xa - xb) * f.i1;
             double s, c;
             sincos(u, &s, &c);
-            double d = s / f.a0;
+            double d = s * f.i0;
             g0 = 4 * d * d;
-            g1 = 4 * d * c * u / f.a0;
+            g1 = 4 * d * c * u * f.i0;
             return;
         }
         case F_MATERN32: {
@@ -124,11 +124,11 @@ __device__ __forceinline__ double factor_dlog_xa(const DevFactor& f, double xa, 
             return -d * f.i0;
         }
         case F_PERIODIC: {
-            double u = GOGP_PI * fabs(r) / f.a1;
+            double u = fabs(r) * f.i1;
             double s, c;
             sincos(u, &s, &c);
-            double d = s / f.a0;
-            return -4 * d * c * GOGP_PI * sg / (f.a0 * f.a1);
+            double d = s * f.i0;
+            return -4 * d * c * sg * f.i0 * f.i1;
         }
         case F_MATERN32: {
             double d = fabs(r) * f.i0;

@@ -140,6 +140,7 @@ void Program::bind(const double* theta, DevProgram* out) const {
             d.a0 = f.p0 >= 0 ? f.s0 * theta[f.p0] : 1.0;
             d.a1 = f.p1 >= 0 ? f.s1 * theta[f.p1] : 0.0;
             d.i0 = 1.0 / d.a0;
+            d.i1 = d.a1 != 0.0 ? 3.14159265358979323846 / d.a1 : 0.0;
             d.c = f.c;
         }
     }

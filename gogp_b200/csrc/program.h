@@ -37,6 +37,7 @@ struct DevFactor {
     int p0, p1;      // theta indices (p1 < 0 when unused)
     double a0, a1;   // effective parameters scale*theta, refreshed per evaluation
     double i0;       // 1 / a0
+    double i1;       // pi / a1 (Periodic: the phase is |r| * i1)
     double c;        // Matern52 d^2 coefficient
 };
 
