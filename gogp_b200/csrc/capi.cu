@@ -1046,7 +1046,16 @@ gogp_status gogp_dev_potrf(gogp_handle* h, double* A, int64_t ld, int64_t n, dou
         void potrf_leaf(double* At, int64_t l, double* w, int b) { CudaBackend::potrf_leaf(At, l, w, b + shift); }
     } be{{pick_stream(h, stream), info, &h->launches, &h->prof, nullptr, 0}, base};
     Blocked<Shifted> bl{be, A, ld, winv, rl_max(), cols_max()};
-    bl.potrf(0, n);
+    // the block is a diagonal block of a distributed matrix and sits on the caller's critical path:
+    // tile-level look-ahead (the handle's bulk streams fork from and join the caller's stream)
+    int64_t nb[3];
+    la_blocks(nb);
+    if (nb[2] >= TILE && !h->prof.on) {
+        bl.la_nb[2] = nb[2];
+        for (auto& l : h->la) l.pending = l.below_pending = false;
+        be.la = h->la;
+    }
+    bl.potrf_la(0, n, 0);
     CK(cudaGetLastError());
     return GOGP_OK;
 }
