@@ -6,7 +6,18 @@
 // log-derivatives so a product term needs only its value:
 //     d(prod)/d log(theta_q) = prod * theta_q * (d f/d theta_q) / f
 #pragma once
+#include <cmath>
+
 #include "program.h"
+
+// The element functions are plain arithmetic: under nvcc they are host + device (the kernels
+// use the device side), under a host compiler they are ordinary inline functions, so the CPU
+// test tier can evaluate the lowered program with exactly this code (tests/cpu_kexpr_backend.cc).
+#if defined(__CUDACC__)
+#define GOGP_HD __host__ __device__ __forceinline__
+#else
+#define GOGP_HD inline
+#endif
 
 namespace gogp {
 
@@ -18,7 +29,7 @@ namespace gogp {
 // i1 = pi/(scale*theta_p) (d differs from the reference's r/l by at most an ulp or two).
 // tutorial/events/kernel/kernel.go:33-44: order the pair, the first event whose from- or to-boundary
 // lies in (lo, hi] discounts the similarity.
-__device__ __forceinline__ double events_value(const DevProgram& prog, double xa, double xb) {
+GOGP_HD double events_value(const DevProgram& prog, double xa, double xb) {
     const double lo = xa > xb ? xb : xa, hi = xa > xb ? xa : xb;
     for (int e = 0; e < prog.nevents; ++e) {
         const double from = prog.ev[e][0], to = prog.ev[e][1];
@@ -27,7 +38,7 @@ __device__ __forceinline__ double events_value(const DevProgram& prog, double xa
     return 1.0;
 }
 
-__device__ __forceinline__ double factor_value(const DevFactor& f, double xa, double xb) {
+GOGP_HD double factor_value(const DevFactor& f, double xa, double xb) {
     switch (f.kind) {
         case F_PARAM:
             return f.a0;
@@ -54,7 +65,7 @@ __device__ __forceinline__ double factor_value(const DevFactor& f, double xa, do
 // coordinate.  The leading Normal factors of a term (the host sorts them first)
 // share one exponential: prod_d exp(-d_d^2/2) = exp(-(sum_d d_d^2)/2).
 template <class XA, class XB>
-__device__ __forceinline__ double term_value(const DevProgram& prog, int t, XA xa, XB xb) {
+GOGP_HD double term_value(const DevProgram& prog, int t, XA xa, XB xb) {
     double p = prog.coef[t];
     int fi = prog.fbeg[t];
     const int fn = fi + prog.nnorm[t], fe = prog.fbeg[t + 1];
@@ -75,7 +86,7 @@ __device__ __forceinline__ double term_value(const DevProgram& prog, int t, XA x
 }
 
 // theta_q * (d f / d theta_q) / f for the (up to) two parameters of a factor.
-__device__ __forceinline__ void factor_dlog_theta(const DevFactor& f, double xa, double xb, double& g0, double& g1) {
+GOGP_HD void factor_dlog_theta(const DevFactor& f, double xa, double xb, double& g0, double& g1) {
     g1 = 0.0;
     switch (f.kind) {
         case F_EVENTS:
@@ -112,7 +123,7 @@ __device__ __forceinline__ void factor_dlog_theta(const DevFactor& f, double xa,
 }
 
 // (d f / d xa) / f ;  d/d xb is its negative for every stock (stationary) leaf.
-__device__ __forceinline__ double factor_dlog_xa(const DevFactor& f, double xa, double xb) {
+GOGP_HD double factor_dlog_xa(const DevFactor& f, double xa, double xb) {
     double r = xa - xb;
     double sg = (r > 0) - (r < 0);
     switch (f.kind) {
@@ -141,6 +152,7 @@ __device__ __forceinline__ double factor_dlog_xa(const DevFactor& f, double xa, 
     }
 }
 
+#if defined(__CUDACC__)
 // ---- TMA (bulk async copy) + mbarrier helpers -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -182,5 +194,6 @@ __device__ __forceinline__ void lower_tile(int b, int& ti, int& tj) {
     ti = t;
     tj = b - t * (t + 1) / 2;
 }
+#endif  // __CUDACC__
 
 }  // namespace gogp
