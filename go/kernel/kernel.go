@@ -146,6 +146,10 @@ func evalHost(ops []gp.Op, x []float64, ntheta int) float64 {
 			}
 			d := math.Abs(xa-xb) / l
 			st = append(st, (1+2.2360679774997900*d+c*d*d)*math.Exp(-2.2360679774997900*d))
+		case opEvents:
+			// the event table lives with the GP (gp.GP.SetEvents), not with the expression: the
+			// host-side convenience evaluates the undiscounted kernel
+			st = append(st, 1)
 		}
 	}
 	return st[0]
