@@ -11,12 +11,10 @@ The Go wrapper a maintainer would add is go/gp/gp.go; this
 module is what can be executed where no Go toolchain exists.
 """
 import ctypes as C
-import math
 
 import numpy as np
 
 from . import _lib
-from . import kernel as _kernel
 
 
 class GoGPError(Exception):

@@ -2,7 +2,6 @@
 gloo ranks + a NumPy compute backend defined here (test infrastructure), against the
 oracle's log marginal likelihood.  On the GPU box the same orchestration runs with the
 CUDA backend (tests/test_gpu_dist.py, tools/dist_bench.py)."""
-import math
 import os
 import socket
 import sys

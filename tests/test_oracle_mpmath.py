@@ -1,7 +1,6 @@
 """50-digit mpmath evaluation of the same formulas, to check the ORACLE itself
 (the Go reference cannot be run here; see oracle/__init__.py)."""
 import mpmath as mp
-import numpy as np
 import pytest
 
 from tests import cases

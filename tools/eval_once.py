@@ -1,7 +1,6 @@
 """One warm-up + `reps` LML+gradient evaluations of the C3 workload at N (for ncu launch lists)."""
 import sys
 
-import numpy as np
 
 sys.path.insert(0, ".")
 import bench
