@@ -314,7 +314,8 @@ void launch_fill_pattern(double* v, int64_t n, cudaStream_t s) {
     if (n > 0) fill_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(v, n, 0.0, 1);
 }
 
-static int g_leaf_variant = -1;  // 0: blocked kernel (shipped), 1: first version (Crout, one barrier per column)
+static int g_leaf_variant = -1;  // 0: blocked kernel (shipped), 1: first version (Crout, one barrier per column),
+                                 // 2: blocked kernel with the shared-memory column broadcast (timing candidate)
 void set_leaf_variant(int v) { g_leaf_variant = v; }
 
 void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s) {
@@ -323,19 +324,22 @@ void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base,
         g_leaf_variant = e ? atoi(e) : 0;
     }
     const size_t smem_crout = (size_t)TILE * LP * sizeof(double);
-    const size_t smem = ((size_t)TILE * LP + 32 * MP) * sizeof(double);
+    const size_t smem = ((size_t)TILE * LP + 32 * MP + 64) * sizeof(double);
     static bool configured[64] = {false};  // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
         cudaFuncSetAttribute(potrf_leaf_crout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_crout);
-        cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(potrf_leaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(potrf_leaf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev & 63] = true;
     }
     if (g_leaf_variant == 1)
         potrf_leaf_crout_kernel<<<1, 512, smem_crout, s>>>(A, ld, winv, info, base);
+    else if (g_leaf_variant == 2)
+        potrf_leaf_kernel<true><<<1, LEAF_THREADS, smem, s>>>(A, ld, winv, info, base);
     else
-        potrf_leaf_kernel<<<1, LEAF_THREADS, smem, s>>>(A, ld, winv, info, base);
+        potrf_leaf_kernel<false><<<1, LEAF_THREADS, smem, s>>>(A, ld, winv, info, base);
 }
 
 void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t s) {

@@ -39,6 +39,10 @@ constexpr int LEAF_THREADS = 384;  // 12 warps: 170 registers each, no spills in
 // C/E1 and D/E2 are independent pairs and share a phase; three CTA barriers per block.
 // Fragment convention as in dgemm.cu: a = A[row fr + 8i][k fk], b = B[col fr + 8j][k fk],
 // acc = C[row fr + 8i][col 2 fk + 8j + {0,1}], fr = lane >> 2, fk = lane & 3.
+// BCAST (variant 2, timing candidate): the scaled column of phase A reaches the other lanes through a
+// 2 x 32-double shared-memory buffer (one store, one __syncwarp, broadcast loads) instead of 2 (31 - j)
+// shuffles per column; same operations on the same values, bit-identical results.
+template <bool BCAST>
 __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, int64_t ld,
                                                             double* __restrict__ winv, int* __restrict__ info,
                                                             int base) {
@@ -74,21 +78,45 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
                 }
             }
             double rinv = 0.0;
+            if (!BCAST) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                double d = __shfl_sync(FULL, a[j], j);
-                if (!(d > 0.0)) {  // not positive definite (or NaN): flag, keep going
-                    if (lane == j) atomicCAS(info, 0, base + o + j + 1);
-                    d = 1.0;
+                for (int j = 0; j < 32; ++j) {
+                    double d = __shfl_sync(FULL, a[j], j);
+                    if (!(d > 0.0)) {  // not positive definite (or NaN): flag, keep going
+                        if (lane == j) atomicCAS(info, 0, base + o + j + 1);
+                        d = 1.0;
+                    }
+                    const double rs = rsqrt(d);
+                    const double l = (lane == j ? d : a[j]) * rs;  // one reciprocal square root, no divide
+                    a[j] = l;
+                    if (lane == j) rinv = rs;
+#pragma unroll
+                    for (int k = j + 1; k < 32; ++k) {
+                        const double lk = __shfl_sync(FULL, l, k);
+                        a[k] = fma(-l, lk, a[k]);
+                    }
                 }
-                const double rs = rsqrt(d);
-                const double l = (lane == j ? d : a[j]) * rs;  // one reciprocal square root, no divide
-                a[j] = l;
-                if (lane == j) rinv = rs;
+            } else {
+                double* colbuf = Mb + 32 * MP;  // [2][32], after the side buffer
 #pragma unroll
-                for (int k = j + 1; k < 32; ++k) {
-                    const double lk = __shfl_sync(FULL, l, k);
-                    a[k] = fma(-l, lk, a[k]);
+                for (int j = 0; j < 32; ++j) {
+                    double d = __shfl_sync(FULL, a[j], j);
+                    if (!(d > 0.0)) {
+                        if (lane == j) {
+                            atomicCAS(info, 0, base + o + j + 1);
+                            a[j] = 1.0;
+                        }
+                        d = 1.0;
+                    }
+                    const double rs = rsqrt(d);
+                    const double l = a[j] * rs;
+                    a[j] = l;
+                    if (lane == j) rinv = rs;
+                    double* cb = colbuf + (j & 1) * 32;  // column j+2 reuses this half: every lane is past j+1's barrier by then
+                    cb[lane] = l;
+                    __syncwarp();
+#pragma unroll
+                    for (int k = j + 1; k < 32; ++k) a[k] = fma(-l, cb[k], a[k]);
                 }
             }
             {

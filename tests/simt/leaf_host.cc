@@ -12,10 +12,13 @@ constexpr int LP = 132;  // as in leaf.cu
 extern "C" {
 
 // A: 128 x 128 row-major with leading dimension ld, factored in place; winv: 128 x 128; *info as the kernel leaves it.
-void simt_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base) {
+void simt_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, int variant) {
     using namespace gogp;
-    const size_t smem = ((size_t)TILE * LP + 32 * MP) * sizeof(double);
-    simt::launch(1, LEAF_THREADS, smem, [&] { potrf_leaf_kernel(A, ld, winv, info, base); });
+    const size_t smem = ((size_t)TILE * LP + 32 * MP + 64) * sizeof(double);
+    if (variant == 2)
+        simt::launch(1, LEAF_THREADS, smem, [&] { potrf_leaf_kernel<true>(A, ld, winv, info, base); });
+    else
+        simt::launch(1, LEAF_THREADS, smem, [&] { potrf_leaf_kernel<false>(A, ld, winv, info, base); });
 }
 
 // out = L^-1 rhs (transposed = 0) or L^-T rhs (1); L: Npad x Npad lower, winv: T tile inverses; sync: T+1 words.

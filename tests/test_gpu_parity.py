@@ -288,10 +288,10 @@ def test_lookahead_factorisation_matches_recursion_and_oracle(nb, monkeypatch):
     assert np.abs(out["0"][1] - out[nb][1]).max() < 1e-11
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_tile_kernel_against_numpy(variant):
-    """The 128 x 128 tile kernel alone (blocked shipped version and the first version): factor,
-    inverse, and the index of the first bad pivot."""
+    """The 128 x 128 tile kernel alone (0: blocked shipped version, 1: the first version, 2: blocked with
+    the shared-memory column broadcast): factor, inverse, and the index of the first bad pivot."""
     import ctypes as C
     from gogp_b200 import _lib
     dg = cases.make_device_gp("c2_rbf")

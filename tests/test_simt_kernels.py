@@ -27,22 +27,26 @@ def simt():
     return C.CDLL(so)
 
 
-def _leaf(simt, A, ld=128, base=0):
+def _leaf(simt, A, ld=128, base=0, variant=0):
     buf = np.full((128, ld), np.nan)
     buf[:, :128] = A
     W = np.zeros((128, 128))
     info = C.c_int(0)
-    simt.simt_potrf_leaf(buf.ctypes.data_as(dp), C.c_int64(ld), W.ctypes.data_as(dp), C.byref(info), base)
+    simt.simt_potrf_leaf(buf.ctypes.data_as(dp), C.c_int64(ld), W.ctypes.data_as(dp), C.byref(info), base, variant)
     return buf[:, :128].copy(), W, info.value
 
 
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("ld,shift", [(128, 1.0), (384, 1e-3)])
-def test_tile_kernel_source_on_the_emulator(simt, ld, shift):
+def test_tile_kernel_source_on_the_emulator(simt, ld, shift, variant):
     rng = np.random.default_rng(int(ld))
     G = rng.standard_normal((128, 128))
     K = G @ G.T / 128 + shift * np.eye(128)
     A = np.tril(K) + np.triu(rng.standard_normal((128, 128)), 1)   # the upper triangle must be ignored
-    Lo, W, info = _leaf(simt, A, ld)
+    Lo, W, info = _leaf(simt, A, ld, variant=variant)
+    if variant == 2:   # same operations on the same values as the shipped variant: bit-identical
+        L0, W0, _ = _leaf(simt, A, ld, variant=0)
+        assert np.array_equal(Lo, L0) and np.array_equal(W, W0)
     ref = np.linalg.cholesky(K)
     cond = np.linalg.cond(ref)
     assert info == 0
@@ -55,8 +59,9 @@ def test_tile_kernel_flags_the_first_bad_pivot(simt):
     for bad in (0, 40, 127):
         K = 2.0 * np.eye(128)
         K[bad, bad] = -1.0
-        _, _, info = _leaf(simt, K, base=256)
-        assert info == 256 + bad + 1
+        for variant in (0, 2):
+            _, _, info = _leaf(simt, K, base=256, variant=variant)
+            assert info == 256 + bad + 1
 
 
 def test_chained_solves_source_on_the_emulator(simt):
