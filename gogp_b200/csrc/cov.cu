@@ -1,5 +1,6 @@
 // Covariance-side kernels: K(X,X)+noise build, K(X,Z) cross build, prior
-// variance, the fused gradient trace and the input gradient.
+// variance, the fused gradient trace and the input gradient.  The kernels themselves are in
+// cov_kernels.cuh (shared with the CPU test tier); this file holds their launchers.
 //
 // Reference semantics: gp/gp.go:109-156 (cov closure), :220-225 (K.SetSym over
 // j >= i), :270-278 and :322-332 (Produce), :434-486 (Gradient).  HBM-bound by
@@ -14,12 +15,7 @@
 
 namespace gogp {
 
-__global__ void transpose_x_kernel(const double* __restrict__ X, double* __restrict__ Xt, int64_t N, int64_t Npad,
-                                   int D) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= Npad) return;
-    for (int d = 0; d < D; ++d) Xt[d * Npad + i] = i < N ? X[i * D + d] : 0.0;
-}
+#include "cov_kernels.cuh"
 
 void launch_transpose_x(const double* X, double* Xt, int64_t N, int64_t Npad, int D, cudaStream_t s) {
     int threads = 256;
@@ -27,92 +23,9 @@ void launch_transpose_x(const double* X, double* Xt, int64_t N, int64_t Npad, in
     transpose_x_kernel<<<blocks, threads, 0, s>>>(X, Xt, N, Npad, D);
 }
 
-// Stage the coordinates of one row tile and one column tile: [D][128] each.
-__device__ __forceinline__ void stage_tiles(double* xr, double* xc, uint64_t* bar, const double* Rt, int64_t ldr,
-                                            int64_t row0, const double* Ct, int64_t ldc, int64_t col0, int D) {
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, (uint32_t)(2 * D * TILE * sizeof(double)));
-        for (int d = 0; d < D; ++d) {
-            tma_load_1d(xr + d * TILE, Rt + d * ldr + row0, TILE * sizeof(double), bar);
-            tma_load_1d(xc + d * TILE, Ct + d * ldc + col0, TILE * sizeof(double), bar);
-        }
-    }
-    mbar_wait(bar, 0);
-}
-
-__device__ __forceinline__ double eval_program(const DevProgram& prog, const double* xc, int c, const double* xr,
-                                               int r) {
-    double k = 0.0;
-    auto xa = [&](int d) { return xc[d * TILE + c]; };
-    auto xb = [&](int d) { return xr[d * TILE + r]; };
-    for (int t = 0; t < prog.nterms; ++t) k += term_value(prog, t, xa, xb);
-    return k;
-}
-
-// out[row][col] = k(xa = C[col], xb = R[row]).  SYM: lower tiles of a square
-// matrix, + noise on the diagonal, identity in the padding; otherwise a full
-// rectangle with zero padding.
-template <bool SYM>
-__global__ void __launch_bounds__(256) cov_tile_kernel(const __grid_constant__ DevProgram prog,
-                                                       const double* __restrict__ Rt, int64_t ldr, int64_t nrows,
-                                                       const double* __restrict__ Ct, int64_t ldc, int64_t ncols,
-                                                       int D, double noise, double* __restrict__ out, int64_t ld,
-                                                       int tiles_n) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* xr = reinterpret_cast<double*>(smem_raw);
-    double* xc = xr + D * TILE;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(xc + D * TILE);
-
-    int ti, tj;
-    if (SYM) {
-        lower_tile(blockIdx.x, ti, tj);
-    } else {
-        ti = blockIdx.x / tiles_n;
-        tj = blockIdx.x % tiles_n;
-    }
-    const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
-    stage_tiles(xr, xc, bar, Rt, ldr, row0, Ct, ldc, col0, D);
-
-    const int c0 = 2 * (threadIdx.x & 63);
-    const int ir = threadIdx.x >> 6;
-    for (int rr = 0; rr < TILE / 4; ++rr) {
-        const int r = rr * 4 + ir;
-        const int64_t gi = row0 + r, gj = col0 + c0;
-        double2 v;
-        v.x = eval_program(prog, xc, c0, xr, r);
-        v.y = eval_program(prog, xc, c0 + 1, xr, r);
-        if (SYM) {
-            if (gi == gj) v.x += noise;
-            if (gi == gj + 1) v.y += noise;
-            if (gi >= nrows || gj >= ncols) v.x = (gi == gj) ? 1.0 : 0.0;
-            if (gi >= nrows || gj + 1 >= ncols) v.y = (gi == gj + 1) ? 1.0 : 0.0;
-        } else {
-            if (gi >= nrows || gj >= ncols) v.x = 0.0;
-            if (gi >= nrows || gj + 1 >= ncols) v.y = 0.0;
-        }
-        *reinterpret_cast<double2*>(out + gi * ld + gj) = v;
-    }
-}
-
 static size_t cov_smem(int D) { return (size_t)2 * D * TILE * sizeof(double) + 16; }
 
-// ---- specialised element loop ("fast shape") ----------------------------------------
-// ncu showed the interpreted kernels above to be bound by instruction issue, not by HBM: ~185
-// instructions per element for a 1-D RBF, ~40 of them the FP64 exp.  When the program is ONE
-// product term whose leading factors are NN Normal leaves (the ARD kernels of every BASELINE
-// config but hyperpriors), the Normal part is unrolled at compile time with the factor constants
-// and the thread's own column coordinates hoisted into registers, and tiles that lie strictly
-// below the diagonal and inside the data skip the per-element diagonal / padding masks.  The
-// remaining factors (parameters, at most a few other leaves) keep the generic factor_value.
-// Same operations in the same order as term_value: bit-identical to the interpreted kernel.
-// Measured at N = 32768: 1-D RBF build 2.97 -> 1.71 ms (2.5 TB/s), C3 kernel 6.6 -> 4.7 ms.  The
-// same treatment of the trace kernel (all-register, one element at a time) measured SLOWER than
-// the staged interpreter (3.7 -> 4.3 ms RBF, 11.3 -> 12.1 ms C3: the 8-element batches of the
-// interpreter overlap their exp latencies) and was dropped.
-constexpr int kFastMaxRest = 4;
-
+// ---- specialised element loop ("fast shape", cov_tile_fast_kernel in cov_kernels.cuh): dispatch ----
 static int fast_elem_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -128,82 +41,6 @@ static int fast_shape(const DevProgram& prog) {
     if (rest < 0 || rest > kFastMaxRest) return -1;
     if (nn == 0 || nn == 1 || nn == 2 || nn == 3 || nn == 4 || nn == 8) return nn;
     return -1;
-}
-
-template <int NN, bool SYM>
-__global__ void __launch_bounds__(256) cov_tile_fast_kernel(const __grid_constant__ DevProgram prog,
-                                                            const double* __restrict__ Rt, int64_t ldr, int64_t nrows,
-                                                            const double* __restrict__ Ct, int64_t ldc, int64_t ncols,
-                                                            int D, double noise, double* __restrict__ out, int64_t ld,
-                                                            int tiles_n) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* xr = reinterpret_cast<double*>(smem_raw);
-    double* xc = xr + D * TILE;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(xc + D * TILE);
-
-    int ti, tj;
-    if (SYM) {
-        lower_tile(blockIdx.x, ti, tj);
-    } else {
-        ti = blockIdx.x / tiles_n;
-        tj = blockIdx.x % tiles_n;
-    }
-    const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
-    stage_tiles(xr, xc, bar, Rt, ldr, row0, Ct, ldc, col0, D);
-
-    const int c0 = 2 * (threadIdx.x & 63);
-    const int ir = threadIdx.x >> 6;
-    constexpr int NR = NN > 0 ? NN : 1;
-    double inv[NR], ca0[NR], ca1[NR];
-    int rofs[NR];
-#pragma unroll
-    for (int j = 0; j < NN; ++j) {
-        const DevFactor& f = prog.f[j];
-        inv[j] = f.i0;
-        rofs[j] = f.dim * TILE;
-        ca0[j] = xc[rofs[j] + c0];
-        ca1[j] = xc[rofs[j] + c0 + 1];
-    }
-    const double coef = prog.coef[0];
-    const int fe = prog.fbeg[1];
-    const bool interior = (SYM ? ti > tj : true) && row0 + TILE <= nrows && col0 + TILE <= ncols;
-    for (int rr = 0; rr < TILE / 4; ++rr) {
-        const int r = rr * 4 + ir;
-        double q0 = 0.0, q1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < NN; ++j) {
-            const double xb = xr[rofs[j] + r];
-            const double d0 = (ca0[j] - xb) * inv[j], d1 = (ca1[j] - xb) * inv[j];
-            q0 = fma(d0, d0, q0);
-            q1 = fma(d1, d1, q1);
-        }
-        double2 v;
-        v.x = coef;
-        v.y = coef;
-        if (NN > 0) {
-            v.x *= exp(-q0 / 2);
-            v.y *= exp(-q1 / 2);
-        }
-        for (int fi = NN; fi < fe; ++fi) {
-            const DevFactor& f = prog.f[fi];
-            const double xb = xr[f.dim * TILE + r], xa0 = xc[f.dim * TILE + c0], xa1 = xc[f.dim * TILE + c0 + 1];
-            v.x *= (f.kind == F_EVENTS) ? events_value(prog, xa0, xb) : factor_value(f, xa0, xb);
-            v.y *= (f.kind == F_EVENTS) ? events_value(prog, xa1, xb) : factor_value(f, xa1, xb);
-        }
-        const int64_t gi = row0 + r, gj = col0 + c0;
-        if (!interior) {
-            if (SYM) {
-                if (gi == gj) v.x += noise;
-                if (gi == gj + 1) v.y += noise;
-                if (gi >= nrows || gj >= ncols) v.x = (gi == gj) ? 1.0 : 0.0;
-                if (gi >= nrows || gj + 1 >= ncols) v.y = (gi == gj + 1) ? 1.0 : 0.0;
-            } else {
-                if (gi >= nrows || gj >= ncols) v.x = 0.0;
-                if (gi >= nrows || gj + 1 >= ncols) v.y = 0.0;
-            }
-        }
-        *reinterpret_cast<double2*>(out + gi * ld + gj) = v;
-    }
 }
 
 template <bool SYM>
@@ -230,7 +67,6 @@ static bool launch_cov_fast(int ntiles, size_t smem, cudaStream_t s, const DevPr
 #undef GOGP_COV_FAST
     return false;
 }
-
 
 void launch_cov_build(const DevProgram& prog, const double* Xt, int64_t N, int64_t Npad, int D, double noise,
                       double* out, cudaStream_t s) {
@@ -274,16 +110,6 @@ void launch_cov_cross(const DevProgram& prog, const double* Xt, int64_t N, int64
     cov_tile_kernel<false><<<tm * tn, 256, smem, s>>>(prog, Zt, Mpad, M, Xt, Npad, N, D, 0.0, out, Npad, tn);
 }
 
-__global__ void cov_self_kernel(const __grid_constant__ DevProgram prog, const double* __restrict__ Zt, int64_t M,
-                                int64_t Mpad, double* __restrict__ kss) {
-    int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    double k = 0.0;
-    auto z = [&](int d) { return Zt[d * Mpad + m]; };
-    for (int t = 0; t < prog.nterms; ++t) k += term_value(prog, t, z, z);
-    kss[m] = k;
-}
-
 void launch_cov_self(const DevProgram& prog, const double* Zt, int64_t M, int64_t Mpad, int D, double* kss,
                      cudaStream_t s) {
     (void)D;
@@ -292,149 +118,7 @@ void launch_cov_self(const DevProgram& prog, const double* Zt, int64_t M, int64_
     if (blocks > 0) cov_self_kernel<<<blocks, threads, 0, s>>>(prog, Zt, M, Mpad, kss);
 }
 
-// ---- fused gradient trace ----------------------------------------------------------
-// One CTA per lower tile; a thread owns a column pair and 32 rows, walked in chunks of
-// 4 rows (E = 8 elements).  For each product term: phase 1 forms w_e * W_e * P_e (term
-// value weighted by W = alpha alpha^T - K^-1 and by 1 below / 1/2 on the diagonal) per
-// element; phase 2 runs over the term's factors and adds the P-weighted log-derivatives
-// to per-thread accumulators, one shared-memory cell per (parameter slot, thread), so
-// nothing is reduced across threads until the end of the tile.  dK is never
-// materialised (the reference stores one dense N x N matrix per parameter,
-// gp/gp.go:93-97,158-163).  ~70 KB of shared memory -> 3 CTAs per SM.
-constexpr int GT_E = 8;
-
-__global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__ DevProgram prog,
-                                                         const double* __restrict__ Xt, int64_t ldx,
-                                                         const double* __restrict__ alpha,
-                                                         const double* __restrict__ kinv, int64_t ld,
-                                                         const double* __restrict__ kdiag, int64_t N, int D,
-                                                         double* __restrict__ partial, int rect_cols,
-                                                         int64_t grow0, int64_t gcol0) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* xr = reinterpret_cast<double*>(smem_raw);
-    double* xc = xr + D * TILE;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(xc + D * TILE);
-    double* pw = reinterpret_cast<double*>(bar + 2);  // [GT_E][256] weighted term values
-    double* ww = pw + GT_E * 256;                     // [GT_E][256] weights w_e * W_e
-    double* acc = ww + GT_E * 256;                    // [ntheta + 1][256] per-thread accumulators
-
-    // whole matrix: lower tiles, diagonal tiles in kdiag.  Block of a distributed matrix
-    // (rect_cols > 0): every tile of a rows x cols block whose origin is element (grow0, gcol0)
-    // of the global matrix; kinv points at the block and holds its diagonal tiles too.
-    int ti, tj;
-    if (rect_cols > 0) {
-        ti = blockIdx.x / rect_cols;
-        tj = blockIdx.x % rect_cols;
-    } else {
-        lower_tile(blockIdx.x, ti, tj);
-    }
-    const int64_t lrow0 = (int64_t)ti * TILE, lcol0 = (int64_t)tj * TILE;
-    const int64_t row0 = grow0 + lrow0, col0 = gcol0 + lcol0;
-    const int tid = threadIdx.x;
-    const int nslot = prog.ntheta;  // slot ntheta = trace of W
-    if (col0 > row0 + TILE - 1) {   // a tile above the diagonal (upper part of a diagonal block): nothing counts
-        if (tid <= nslot) partial[(int64_t)blockIdx.x * (nslot + 1) + tid] = 0.0;
-        return;
-    }
-    for (int q = 0; q <= nslot; ++q) acc[q * 256 + tid] = 0.0;
-    stage_tiles(xr, xc, bar, Xt, ldx, row0, Xt, ldx, col0, D);
-
-    const bool side_diag = kdiag != nullptr && ti == tj;
-    const double* ktile = side_diag ? kdiag + (int64_t)ti * TILE * TILE : kinv + lrow0 * ld + lcol0;
-    const int64_t kld = side_diag ? TILE : ld;
-    const int c0 = 2 * (tid & 63);
-    const int ir = tid >> 6;
-    const int64_t gj = col0 + c0;
-    const double aj0 = alpha[gj], aj1 = alpha[gj + 1];
-    double trw = 0.0;
-
-    for (int chunk = 0; chunk < 2 * TILE / (4 * GT_E); ++chunk) {
-        // weights w_e * W_e of this chunk (1 below the diagonal, 1/2 on it, 0 elsewhere)
-#pragma unroll
-        for (int e = 0; e < GT_E; e += 2) {
-            const int r = (chunk * (GT_E / 2) + (e >> 1)) * 4 + ir;
-            const int64_t gi = row0 + r;
-            const double2 kv = *reinterpret_cast<const double2*>(ktile + (int64_t)r * kld + c0);
-            const double ai = alpha[gi];
-            double w0 = 0.0, w1 = 0.0;
-            if (gi < N && gj < N && gi >= gj) {
-                const double W = ai * aj0 - kv.x;
-                if (gi == gj) {
-                    trw += W;
-                    w0 = 0.5 * W;
-                } else {
-                    w0 = W;
-                }
-            }
-            if (gi < N && gj + 1 < N && gi >= gj + 1) {
-                const double W = ai * aj1 - kv.y;
-                if (gi == gj + 1) {
-                    trw += W;
-                    w1 = 0.5 * W;
-                } else {
-                    w1 = W;
-                }
-            }
-            ww[e * 256 + tid] = w0;
-            ww[(e + 1) * 256 + tid] = w1;
-        }
-        for (int t = 0; t < prog.nterms; ++t) {
-            const int fb = prog.fbeg[t], fe = prog.fbeg[t + 1];
-            // phase 1: weighted term values
-            for (int e = 0; e < GT_E; ++e) {
-                const int r = (chunk * (GT_E / 2) + (e >> 1)) * 4 + ir;
-                const int c = c0 + (e & 1);
-                auto xa = [&](int d) { return xc[d * TILE + c]; };
-                auto xb = [&](int d) { return xr[d * TILE + r]; };
-                const double w = ww[e * 256 + tid];
-                pw[e * 256 + tid] = (w != 0.0) ? w * term_value(prog, t, xa, xb) : 0.0;
-            }
-            // phase 2: per-factor log-derivatives
-            for (int fi = fb; fi < fe; ++fi) {
-                const DevFactor& f = prog.f[fi];
-                if (f.p0 < 0) continue;  // parameter-free factor (events)
-                double s0 = 0.0, s1 = 0.0;
-                for (int e = 0; e < GT_E; ++e) {
-                    const int r = (chunk * (GT_E / 2) + (e >> 1)) * 4 + ir;
-                    const int c = c0 + (e & 1);
-                    double g0, g1;
-                    factor_dlog_theta(f, xc[f.dim * TILE + c], xr[f.dim * TILE + r], g0, g1);
-                    const double p = pw[e * 256 + tid];
-                    s0 = fma(p, g0, s0);
-                    s1 = fma(p, g1, s1);
-                }
-                acc[f.p0 * 256 + tid] += s0;
-                if (f.p1 >= 0) acc[f.p1 * 256 + tid] += s1;
-            }
-        }
-    }
-    acc[nslot * 256 + tid] = trw;
-    __syncthreads();
-    // fixed-order tree over the 256 threads of each slot (bit-repeatable)
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o)
-            for (int q = 0; q <= nslot; ++q) acc[q * 256 + tid] += acc[q * 256 + tid + o];
-        __syncthreads();
-    }
-    if (tid <= nslot) partial[(int64_t)blockIdx.x * (nslot + 1) + tid] = acc[tid * 256];
-}
-
-// Deterministic second stage: one CTA per slot, fixed summation order.
-__global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restrict__ partial, int nblocks, int nslots,
-                                                          double* __restrict__ out, int accumulate) {
-    __shared__ double sh[256];
-    const int q = blockIdx.x;
-    double s = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * nslots + q];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[q] = accumulate ? out[q] + sh[0] : sh[0];
-}
-
+// ---- fused gradient trace: launchers (kernel and its description in cov_kernels.cuh) ----
 void launch_grad_trace(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,
                        const double* kdiag, int64_t N, int64_t Npad, int D, double* partial, double* out,
                        cudaStream_t s) {
@@ -458,51 +142,6 @@ void launch_grad_trace_block(const DevProgram& prog, const double* Xt, int64_t l
     grad_trace_kernel<<<ntiles, 256, smem, s>>>(prog, Xt, ldx, alpha, kinv, ld, nullptr, N, D, partial, ctiles, grow0,
                                                 gcol0);
     grad_reduce_kernel<<<prog.ntheta + 1, 256, 0, s>>>(partial, ntiles, prog.ntheta + 1, out, 1);
-}
-
-// ---- input gradient (with_obs) ---------------------------------------------------
-// One CTA per observation i; for each coordinate d a block reduction over j != i of
-// W_ij * d k(x_i, x_j) / d x_{i,d}.  O(N^2 D F); the reference needs N*D dense
-// N x N matrices and 4N^3 flops each for the same numbers (gp/gp.go:93-94,118-129).
-__global__ void __launch_bounds__(256) grad_inputs_kernel(const __grid_constant__ DevProgram prog,
-                                                          const double* __restrict__ Xt, int64_t ldx,
-                                                          const double* __restrict__ alpha,
-                                                          const double* __restrict__ kinv, int64_t ld,
-                                                          const double* __restrict__ kdiag, int64_t N, int D,
-                                                          double* __restrict__ gx) {
-    __shared__ double sh[256];
-    const int64_t i = blockIdx.x;
-    const double ai = alpha[i];
-    for (int d = 0; d < D; ++d) {
-        double s = 0.0;
-        for (int64_t j = threadIdx.x; j < N; j += 256) {
-            if (j == i) continue;
-            const int64_t hi = i > j ? i : j, lo = i > j ? j : i;
-            const int64_t th = hi / TILE, tl = lo / TILE;
-            double kv = (th == tl) ? kdiag[th * TILE * TILE + (hi % TILE) * TILE + (lo % TILE)] : kinv[hi * ld + lo];
-            const double W = ai * alpha[j] - kv;
-            double dk = 0.0;
-            auto xa = [&](int dd) { return Xt[dd * ldx + i]; };
-            auto xb = [&](int dd) { return Xt[dd * ldx + j]; };
-            for (int t = 0; t < prog.nterms; ++t) {
-                double g = 0.0;
-                for (int fi = prog.fbeg[t]; fi < prog.fbeg[t + 1]; ++fi) {
-                    const DevFactor& f = prog.f[fi];
-                    if (f.dim == d && f.kind != F_PARAM) g += factor_dlog_xa(f, xa(d), xb(d));
-                }
-                if (g != 0.0) dk += term_value(prog, t, xa, xb) * g;
-            }
-            s += W * dk;
-        }
-        sh[threadIdx.x] = s;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) gx[i * D + d] = sh[0];
-        __syncthreads();
-    }
 }
 
 void launch_grad_inputs(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,

@@ -186,14 +186,16 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
+#endif  // __CUDACC__
+
 // Lower-triangular tile index b -> (ti, tj), ti >= tj, rows ascending.
-__device__ __forceinline__ void lower_tile(int b, int& ti, int& tj) {
+GOGP_HD void lower_tile(int b, int& ti, int& tj) {
     int t = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
     while (t * (t + 1) / 2 > b) --t;
     while ((t + 1) * (t + 2) / 2 <= b) ++t;
     ti = t;
     tj = b - t * (t + 1) / 2;
 }
-#endif  // __CUDACC__
+
 
 }  // namespace gogp

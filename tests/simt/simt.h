@@ -118,6 +118,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #define __device__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __shared__ static
 #define __align__(n) alignas(n)
 #define threadIdx (simt::ctx.tid)
