@@ -24,172 +24,7 @@ namespace gogp {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
-constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
-constexpr int OPERAND_BYTES = BM * BK * 8;           // 16 KB
-constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;       // A then B
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
-
-struct TmaArgs {
-    double* C;
-    double* cdiag;
-    int64_t ldc;
-    int tm, tn;
-    int k;
-    int mode;
-    double alpha, beta;
-};
-
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-
-__global__ void __launch_bounds__(THREADS, 1)
-    dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                     const TmaArgs g) {
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-byte aligned tiles
-    const uint32_t bars = base + STAGES * STAGE_BYTES;             // full[STAGES] then empty[STAGES]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    int ti, tj;
-    if (g.mode & GEMM_LOWER) {
-        lower_tile(blockIdx.x, ti, tj);
-    } else {
-        constexpr int GROUP_M = 16;  // grouped rasterisation, as in dgemm.cu
-        const int per_group = GROUP_M * g.tn;
-        const int gid = blockIdx.x / per_group, rem = blockIdx.x % per_group;
-        const int first = gid * GROUP_M;
-        const int gsz = (g.tm - first) < GROUP_M ? (g.tm - first) : GROUP_M;
-        ti = first + rem % gsz;
-        tj = rem / gsz;
-    }
-    const int row0 = ti * BM, col0 = tj * BN;
-    const int k_lo = (g.mode & GEMM_KTRI) ? ti * BM : 0;
-    const int nk = (g.k - k_lo) / BK;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * s), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * (STAGES + s)), "r"(CONSUMER_WARPS));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == CONSUMER_WARPS) {
-        // ---- producer: one lane feeds the ring ----
-        if (lane == 0) {
-            for (int kt = 0; kt < nk; ++kt) {
-                const int s = kt % STAGES;
-                if (kt >= STAGES) mbar_wait_u32(bars + 8 * (STAGES + s), ((kt / STAGES) - 1) & 1);
-                const uint32_t full = bars + 8 * s;
-                mbar_expect(full, STAGE_BYTES);
-                const uint32_t dst = base + s * STAGE_BYTES;
-                tma_load_2d(dst, &mapA, k_lo + kt * BK, row0, full);
-                tma_load_2d(dst + OPERAND_BYTES, &mapB, k_lo + kt * BK, col0, full);
-            }
-        }
-        return;
-    }
-
-    // ---- consumers ----
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 64 x 32
-    const int fr = lane >> 2, fk = lane & 3;
-    uint32_t koff[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) koff[s] = (uint32_t)((((((fk >> 1) << 2) + s) ^ fr) << 4) | ((fk & 1) << 3));
-    const uint32_t arow = (uint32_t)((wm * 64 + fr) * 128);
-    const uint32_t brow = (uint32_t)(OPERAND_BYTES + (wn * 32 + fr) * 128);
-
-    double acc[8][4][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    for (int kt = 0; kt < nk; ++kt) {
-        const int s = kt % STAGES;
-        mbar_wait_u32(bars + 8 * s, (kt / STAGES) & 1);
-        const uint32_t st = base + s * STAGE_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            double a[8], b[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(st + arow + i * 8 * 128 + koff[ks]));
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[j]) : "r"(st + brow + j * 8 * 128 + koff[ks]));
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));  // this warp is done with the stage
-    }
-
-    double* Cb;
-    int64_t ldc;
-    if ((g.mode & GEMM_DIAG_OUT) && ti == tj) {
-        Cb = g.cdiag + (int64_t)ti * BM * BN;
-        ldc = BN;
-    } else {
-        Cb = g.C + (int64_t)row0 * g.ldc + col0;
-        ldc = g.ldc;
-    }
-    const int er = wm * 64 + fr, ec = wn * 32 + 2 * fk;
-    if (g.mode & GEMM_INPLACE) {
-        // C aliases A: every consumer warp must have read its last stage before anyone stores
-        asm volatile("bar.sync 1, %0;" ::"r"(CONSUMER_WARPS * 32) : "memory");
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double2* p = reinterpret_cast<double2*>(Cb + (int64_t)(er + i * 8) * ldc + ec + j * 8);
-            double2 v;
-            v.x = g.alpha * acc[i][j][0];
-            v.y = g.alpha * acc[i][j][1];
-            if (g.beta != 0.0) {
-                const double2 c = *p;
-                v.x += g.beta * c.x;
-                v.y += g.beta * c.y;
-            }
-            *p = v;
-        }
-}
+#include "dgemm_tma_kernel.cuh"
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

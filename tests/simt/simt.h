@@ -15,8 +15,11 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <functional>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -26,12 +29,32 @@ struct uint3_t {
     unsigned x = 0, y = 0, z = 0;
 };
 
+// mbarrier (PTX): arrival count + transaction bytes per phase; a phase completes when both reach zero.
+struct MBar {
+    std::mutex m;
+    std::condition_variable cv;
+    int count = 0, pending = 0;
+    long long tx = 0;
+    unsigned phase = 0;
+    void settle() {  // caller holds m
+        if (pending == 0 && tx == 0) {
+            phase ^= 1u;
+            pending = count;
+            cv.notify_all();
+        }
+    }
+};
+
 struct Cta {
     int nthreads = 0, nwarps = 0;
     std::unique_ptr<std::barrier<>> cta_bar;
     std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
     std::vector<double> slot_a, slot_b;  // [nwarps][32] exchange slots of the warp collectives
     std::vector<unsigned char> dyn;
+    unsigned char* dyn_aligned = nullptr;  // 1024-byte aligned (what SWIZZLE_128B tiles need)
+    std::mutex table_m;
+    std::map<unsigned, std::unique_ptr<MBar>> mbars;               // keyed by shared-memory offset
+    std::map<int, std::unique_ptr<std::barrier<>>> named;          // bar.sync id, count
 };
 
 struct Ctx {
@@ -41,7 +64,7 @@ struct Ctx {
 };
 inline thread_local Ctx ctx;
 
-inline void* dyn_smem() { return ctx.cta->dyn.data(); }
+inline void* dyn_smem() { return ctx.cta->dyn_aligned; }
 inline void syncthreads() { ctx.cta->cta_bar->arrive_and_wait(); }
 inline void syncwarp() { ctx.cta->warp_bar[ctx.warp]->arrive_and_wait(); }
 
@@ -72,6 +95,59 @@ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     syncwarp();
 }
 
+// ---- what the TMA GEMM needs: mbarriers, the 2-D tensor copy with 128-byte swizzle, named barriers ----
+inline MBar& mbar_at(unsigned addr) {
+    Cta* c = ctx.cta;
+    std::lock_guard<std::mutex> g(c->table_m);
+    auto& slot = c->mbars[addr];
+    if (!slot) slot = std::make_unique<MBar>();
+    return *slot;
+}
+inline void mbar_init(unsigned addr, int count) {
+    MBar& b = mbar_at(addr);
+    std::lock_guard<std::mutex> g(b.m);
+    b.count = b.pending = count;
+    b.tx = 0;
+    b.phase = 0;
+}
+inline void mbar_arrive(unsigned addr) {
+    MBar& b = mbar_at(addr);
+    std::lock_guard<std::mutex> g(b.m);
+    --b.pending;
+    b.settle();
+}
+inline void mbar_expect_tx(unsigned addr, unsigned bytes) {  // arrive.expect_tx
+    MBar& b = mbar_at(addr);
+    std::lock_guard<std::mutex> g(b.m);
+    b.tx += bytes;
+    --b.pending;
+    b.settle();
+}
+inline void mbar_complete_tx(unsigned addr, unsigned bytes) {
+    MBar& b = mbar_at(addr);
+    std::lock_guard<std::mutex> g(b.m);
+    b.tx -= bytes;
+    b.settle();
+}
+// try_wait.parity in a loop: returns once the phase with the given parity has completed
+inline void mbar_wait(unsigned addr, unsigned parity) {
+    MBar& b = mbar_at(addr);
+    std::unique_lock<std::mutex> g(b.m);
+    b.cv.wait(g, [&] { return (b.phase & 1u) != (parity & 1u); });
+}
+inline double lds_f64(unsigned addr) { return *reinterpret_cast<const double*>(ctx.cta->dyn_aligned + addr); }
+inline void named_barrier(int id, int nthreads) {
+    Cta* c = ctx.cta;
+    std::barrier<>* b;
+    {
+        std::lock_guard<std::mutex> g(c->table_m);
+        auto& slot = c->named[id];
+        if (!slot) slot = std::make_unique<std::barrier<>>((std::ptrdiff_t)nthreads);
+        b = slot.get();
+    }
+    b->arrive_and_wait();
+}
+
 inline unsigned ld_acquire(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void st_release(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 
@@ -88,7 +164,9 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, const std::f
         }
         cta.slot_a.assign((size_t)cta.nwarps * 32, 0.0);
         cta.slot_b.assign((size_t)cta.nwarps * 32, 0.0);
-        cta.dyn.assign(dyn_bytes + 64, 0xFF);  // poison: shared memory starts undefined
+        cta.dyn.assign(dyn_bytes + 2048, 0xFF);  // poison: shared memory starts undefined
+        cta.dyn_aligned = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cta.dyn.data()) + 1023) &
+                                                           ~(uintptr_t)1023);
         std::vector<std::thread> th;
         th.reserve(block);
         for (unsigned t = 0; t < block; ++t)

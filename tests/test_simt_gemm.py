@@ -1,6 +1,9 @@
-"""The cp.async FP64 DMMA GEMM kernel (gogp_b200/csrc/dgemm_kernels.cuh, both shipped CTA shapes, every tile-map
-mode the blocked algebra uses) compiled UNMODIFIED for the host under the SIMT emulator and checked against NumPy.
-The m8n8k4 MMA is the emulator's warp collective with the PTX fragment layout, cp.async an immediate copy."""
+"""Both FP64 DMMA GEMM kernels -- the cp.async one (gogp_b200/csrc/dgemm_kernels.cuh, both shipped CTA shapes) and
+the TMA + mbarrier warp-specialised one (gogp_b200/csrc/dgemm_tma_kernel.cuh) -- compiled UNMODIFIED for the host under
+the SIMT emulator and checked against NumPy in every tile-map mode the blocked algebra uses.  The m8n8k4 MMA is the
+emulator's warp collective with the PTX fragment layout; cp.async is an immediate copy; the emulator models mbarrier
+phases / transaction counts, the 2-D tensor copy with its 128-byte swizzle and the named barrier, so the TMA
+kernel's ring protocol and swizzled fragment addressing run -- and are race-checked under ThreadSanitizer -- on a CPU."""
 import ctypes as C
 import os
 import subprocess
@@ -24,6 +27,19 @@ def gemm():
     L = C.CDLL(so)
     L.simt_dgemm.argtypes = [dp, i64, dp, i64, dp, i64, i64, i64, i64, C.c_double, C.c_double, C.c_int, dp, C.c_int]
     L.simt_dgemm.restype = None
+    return L
+
+
+@pytest.fixture(scope="module")
+def tma():
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libsimt_gemm_tma.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-Wno-unknown-pragmas", "-pthread", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "simt", "gemm_tma_host.cc")])
+    L = C.CDLL(so)
+    L.simt_dgemm_tma.argtypes = [dp, i64, dp, i64, dp, i64, i64, i64, i64, C.c_double, C.c_double, C.c_int, dp]
+    L.simt_dgemm_tma.restype = None
     return L
 
 
@@ -94,3 +110,60 @@ def test_in_place_solve_with_a_diagonal_block(gemm):
     gemm.simt_dgemm(ptr, 384, ptr, 384, _p(W), 128, m, 128, 128, 1.0, 0.0, INPLACE, None, 0)
     assert np.abs(view - ref).max() <= 1e-13 * np.abs(ref).max()
     assert np.array_equal(Bm[:, :128], keep[:, :128]) and np.array_equal(Bm[:, 256:], keep[:, 256:])
+
+
+def test_tma_kernel_full_update_with_a_wrapping_ring(tma):
+    rng = np.random.default_rng(40)
+    m, n, k = 128, 256, 512                                   # 32 k-tiles through a 6-stage ring
+    A, B = rng.standard_normal((m, k + 32))[:, 16:16 + k], rng.standard_normal((n, k))   # offset, strided view of A
+    Cm = rng.standard_normal((m, n))
+    ref = 0.25 * Cm - 1.0 * (A @ B.T)
+    ptr = C.cast(A.ctypes.data, dp)
+    tma.simt_dgemm_tma(_p(Cm), n, ptr, A.strides[0] // 8, _p(B), k, m, n, k, -1.0, 0.25, FULL, None)
+    assert np.abs(Cm - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_tma_kernel_lauum_modes(tma):
+    rng = np.random.default_rng(41)
+    n = 256
+    U = np.triu(rng.standard_normal((n, n)))
+    Up = U + np.tril(np.full((n, n), np.nan), -129)
+    Cm = np.full((n, n), np.nan)
+    Cm[:128, 128:] = 7.0
+    cdiag = np.full((2, 128, 128), np.nan)
+    tma.simt_dgemm_tma(_p(Cm), n, _p(Up), n, _p(Up), n, n, n, n, 1.0, 0.0, LOWER | KTRI | DIAG_OUT, _p(cdiag))
+    ref = U @ U.T
+    assert np.abs(Cm[128:, :128] - ref[128:, :128]).max() <= 1e-13 * np.abs(ref).max()
+    assert np.all(Cm[:128, 128:] == 7.0)
+    for t in range(2):
+        assert np.abs(cdiag[t] - ref[t * 128:(t + 1) * 128, t * 128:(t + 1) * 128]).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_tma_kernel_in_place_solve(tma):
+    rng = np.random.default_rng(42)
+    m = 256
+    Bm = rng.standard_normal((m, 384))
+    W = np.tril(rng.standard_normal((128, 128)))
+    ref = Bm[:, 128:256] @ W.T
+    keep = Bm.copy()
+    ptr = C.cast(Bm.ctypes.data + 128 * 8, dp)
+    tma.simt_dgemm_tma(ptr, 384, ptr, 384, _p(W), 128, m, 128, 128, 1.0, 0.0, INPLACE, None)
+    assert np.abs(Bm[:, 128:256] - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.array_equal(Bm[:, :128], keep[:, :128]) and np.array_equal(Bm[:, 256:], keep[:, 256:])
+
+
+def test_tma_ring_protocol_under_thread_sanitizer():
+    """Producer warp / eight consumer warps, full and empty mbarriers, stage reuse: any read of a stage before its
+    data landed, or a refill before every consumer released it, is a reported race."""
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "simt_tsan_tma")
+    simt = os.path.join(ROOT, "tests", "simt")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-Wno-unknown-pragmas", "-pthread", "-o", exe,
+                        os.path.join(simt, "tsan_tma_main.cc"), os.path.join(simt, "gemm_tma_host.cc")],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available: " + r.stderr[-200:])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "data race" not in r.stdout + r.stderr, (r.stdout + r.stderr)[-2000:]
