@@ -296,9 +296,9 @@ func (gp *GP) Gradient() []float64 {
 
 // OptResult reports what Optimize did (gogp_opt_result).
 type OptResult struct {
-	Iters, Evals int
-	LML0, LML    float64
-	Converged    bool
+	Iters, Evals, Grads int
+	LML0, LML           float64
+	Converged           bool
 }
 
 // Optimize runs the tutorial's MLE loop (tutorial/tutorial.go:124-175) inside
@@ -340,5 +340,5 @@ func (gp *GP) Optimize(x []float64, alg string, iters int, threshold, rate float
 			gp.ThetaNoise[i-nts] = math.Exp(x[i])
 		}
 	}
-	return OptResult{int(r.iters), int(r.evals), float64(r.lml0), float64(r.lml), r.converged != 0}, nil
+	return OptResult{int(r.iters), int(r.evals), int(r.grads), float64(r.lml0), float64(r.lml), r.converged != 0}, nil
 }

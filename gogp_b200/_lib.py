@@ -40,7 +40,7 @@ class OptSettings(C.Structure):
 class OptResult(C.Structure):
     """gogp_opt_result"""
     _fields_ = [("iters", C.c_int), ("evals", C.c_int), ("lml0", C.c_double), ("lml", C.c_double),
-                ("converged", C.c_int)]
+                ("converged", C.c_int), ("grads", C.c_int)]
 
 
 PRIOR_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double))

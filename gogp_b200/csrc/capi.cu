@@ -785,30 +785,52 @@ gogp_status gogp_optimize(gogp_handle* h, const gogp_opt_settings* st, double* l
     s.eps = st->eps > 0.0 ? st->eps : 1e-8;
     s.history = st->history > 0 ? st->history : 15;
     gogp_status hard = GOGP_OK;  // anything but "not positive definite" aborts the loop
-    auto eval = [&](const double* x, double* f, double* g) {
+    double prior_ll = 0.0;
+    std::vector<double> prior_g(P > 0 ? P : 1);
+    // value = gp.GP.Observe (+ priors), grad = gp.GP.Gradient (+ priors) at the same point: a trial step the
+    // line search rejects on its value never pays for K^-1
+    auto value = [&](const double* x, double* f) {
         if (hard != GOGP_OK) return false;
         double lml = 0.0;
-        gogp_status e = gogp_observe(h, x, 0, nullptr, nullptr, 0, &lml);
-        if (e == GOGP_OK) e = gogp_gradient(h, g, P);
+        const gogp_status e = gogp_observe(h, x, 0, nullptr, nullptr, 0, &lml);
         if (e != GOGP_OK) {
             if (e != GOGP_NOT_POSITIVE_DEFINITE) hard = e;
             return false;
         }
-        if (prior) lml += prior(ctx, x, P, g);
+        if (prior) {
+            for (int i = 0; i < P; ++i) prior_g[i] = 0.0;
+            prior_ll = prior(ctx, x, P, prior_g.data());
+            lml += prior_ll;
+        }
         *f = lml;
         return true;
     };
+    auto grad = [&](double* g) {
+        if (hard != GOGP_OK) return false;
+        const gogp_status e = gogp_gradient(h, g, P);
+        if (e != GOGP_OK) {
+            hard = e;
+            return false;
+        }
+        if (prior)
+            for (int i = 0; i < P; ++i) g[i] += prior_g[i];
+        return true;
+    };
     std::vector<double> x(log_theta, log_theta + P);
-    const OptResult r = s.method == 0 ? adam_ascent(eval, x, s) : lbfgs_ascent(eval, x, s);
+    const OptResult r = s.method == 0 ? adam_ascent(value, grad, x, s) : lbfgs_ascent(value, grad, x, s);
     result->iters = r.iters;
     result->evals = r.evals;
+    result->grads = r.grads;
     result->lml0 = r.f0;
     result->lml = r.f;
     result->converged = r.converged;
     if (hard != GOGP_OK) return hard;  // h->err was set by the failing call
     if (r.failed) return fail(h, GOGP_NOT_POSITIVE_DEFINITE, "gogp_optimize: the starting point cannot be evaluated");
     for (int i = 0; i < P; ++i) log_theta[i] = x[i];
-    return GOGP_OK;
+    // leave the handle AT the returned point (LML, Gradient, Produce follow from it): free when the last
+    // evaluation was there (the memo answers), one more factorisation if the line search ended on a rejected trial
+    double lml_at = 0.0;
+    return gogp_observe(h, x.data(), 0, nullptr, nullptr, 0, &lml_at);
 }
 
 gogp_status gogp_get_alpha(gogp_handle* h, double* alpha, int64_t N) {

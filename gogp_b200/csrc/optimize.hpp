@@ -14,9 +14,12 @@
 // gogp_observe + gogp_gradient (capi.cu), with X and Y resident in HBM: per iteration only
 // P parameters go down and P + 1 numbers come back.
 //
-// The objective is MAXIMISED (log marginal likelihood + log prior).  eval(x, &f, g) returns
-// false where the reference would panic (covariance not positive definite): the line
-// search treats that as "step too long"; Adam stops there.
+// The objective is MAXIMISED (log marginal likelihood + log prior).  It comes as the reference's own
+// pair: value(x, &f) (gp.GP.Observe + priors: N^3/3 flop) and grad(g) for the point value() was last
+// called at (gp.GP.Gradient: another 2N^3/3).  The line search asks for the gradient only once a
+// trial point has passed the sufficient-decrease test, so a rejected step costs a third of an
+// accepted one.  value() returns false where the reference would panic (covariance not positive
+// definite): the line search treats that as "step too long"; Adam stops there.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -36,7 +39,8 @@ struct OptSettings {
 
 struct OptResult {
     int iters = 0;      // major iterations (Adam steps / L-BFGS directions)
-    int evals = 0;      // objective + gradient evaluations
+    int evals = 0;      // objective evaluations
+    int grads = 0;      // gradient evaluations (<= evals)
     double f0 = 0.0;    // objective at the starting point
     double f = 0.0;     // objective at the returned point
     int converged = 0;  // 1: every |g_i| < threshold
@@ -52,12 +56,17 @@ inline bool below_threshold(const std::vector<double>& g, double thr) {
 // infer.Adam ascent.  On return x is the last point reached and f the objective there (the
 // tutorial's "final log likelihood", tutorial/tutorial.go:171-175); a point that cannot be
 // evaluated is rolled back to its predecessor.
-template <class Eval>
-OptResult adam_ascent(Eval&& eval, std::vector<double>& x, const OptSettings& s) {
+template <class Value, class Grad>
+OptResult adam_ascent(Value&& value, Grad&& grad, std::vector<double>& x, const OptSettings& s) {
     OptResult r;
     const size_t n = x.size();
     std::vector<double> g(n), m(n, 0.0), v(n, 0.0), prev(x);
     double f = 0.0, b1t = 1.0, b2t = 1.0;
+    auto eval = [&](const double* p, double* fo, double* go) {  // Adam always wants both
+        if (!value(p, fo)) return false;
+        ++r.grads;
+        return (bool)grad(go);
+    };
     for (int t = 1; t <= s.max_iters; ++t) {
         ++r.evals;
         if (!eval(x.data(), &f, g.data())) {
@@ -97,23 +106,28 @@ OptResult adam_ascent(Eval&& eval, std::vector<double>& x, const OptSettings& s)
 }
 
 // L-BFGS ascent (internally minimises -f).
-template <class Eval>
-OptResult lbfgs_ascent(Eval&& eval, std::vector<double>& x, const OptSettings& s) {
+template <class Value, class Grad>
+OptResult lbfgs_ascent(Value&& value, Grad&& grad, std::vector<double>& x, const OptSettings& s) {
     OptResult r;
     const size_t n = x.size();
     const int hist = s.history > 0 ? s.history : 15;
     std::vector<double> g(n), xt(n), gt(n), d(n), q(n);
     double f = 0.0;
-    auto neg_eval = [&](const double* p, double* fo, double* go) {
+    auto neg_value = [&](const double* p, double* fo) {
         ++r.evals;
         double fv = 0.0;
-        if (!eval(p, &fv, go)) return false;
+        if (!value(p, &fv)) return false;
         if (!std::isfinite(fv)) return false;
         *fo = -fv;
+        return true;
+    };
+    auto neg_grad = [&](double* go) {  // at the point neg_value was last called with
+        ++r.grads;
+        if (!grad(go)) return false;
         for (size_t i = 0; i < n; ++i) go[i] = -go[i];
         return true;
     };
-    if (!neg_eval(x.data(), &f, g.data())) {
+    if (!neg_value(x.data(), &f) || !neg_grad(g.data())) {
         r.failed = 1;
         return r;
     }
@@ -143,8 +157,8 @@ OptResult lbfgs_ascent(Eval&& eval, std::vector<double>& x, const OptSettings& s
         bool ok = false;
         for (int ls = 0; ls < 40; ++ls) {
             for (size_t i = 0; i < n; ++i) xt[i] = x[i] + t * d[i];
-            const bool evaluated = neg_eval(xt.data(), &ft, gt.data());
-            if (!evaluated || ft > f + c1 * t * gd) {
+            const bool evaluated = neg_value(xt.data(), &ft);
+            if (!evaluated || ft > f + c1 * t * gd || !neg_grad(gt.data())) {  // gradient only past Armijo
                 hi = t;
                 t = 0.5 * (lo + hi);
             } else if (dot(gt, d) < c2 * gd) {

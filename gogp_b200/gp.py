@@ -219,7 +219,7 @@ class GP:
         (optimize.Minimize, tutorial/tutorial.go:131-155) or "adam" (infer.Adam, :156-168); ``iters``,
         ``threshold``, ``rate`` are ITERS, THRESHOLD, RATE.  ``priors`` is gp.Model's Priors (an object
         with Observe(x) and Gradient()) or None.  x (log hyper-parameters, float64) is updated in
-        place; returns a dict with iters, evals, lml0, lml, converged."""
+        place; returns a dict with iters, evals (Observe calls), grads (Gradient calls), lml0, lml, converged."""
         self._defaults()
         h = self._handle()
         L = _lib.lib()
@@ -253,8 +253,8 @@ class GP:
         self._with_obs, self._n = False, n
         self.ThetaSimil = list(np.exp(x[:self._nts()]))
         self.ThetaNoise = list(np.exp(x[self._nts():]))
-        return {"iters": result.iters, "evals": result.evals, "lml0": result.lml0, "lml": result.lml,
-                "converged": bool(result.converged)}
+        return {"iters": result.iters, "evals": result.evals, "grads": result.grads, "lml0": result.lml0,
+                "lml": result.lml, "converged": bool(result.converged)}
 
     # -- extras over the C-ABI ---------------------------------------------------------
     def PhaseTimes(self):

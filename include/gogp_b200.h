@@ -224,10 +224,12 @@ typedef struct {
 } gogp_opt_settings;
 typedef struct {
     int iters;         /* Adam steps / L-BFGS directions taken */
-    int evals;         /* LML + gradient evaluations spent */
+    int evals;         /* LML evaluations spent (Observe: build + Cholesky + solves) */
     double lml0;       /* objective at the starting point */
     double lml;        /* objective at the returned point */
     int converged;     /* 1: gradient threshold met */
+    int grads;         /* gradient evaluations spent (K^-1 + trace); <= evals: a trial step the line search
+                          rejects on its value alone never computes K^-1 */
 } gogp_opt_result;
 typedef double (*gogp_prior_fn)(void* ctx, const double* x, int64_t n, double* grad);
 gogp_status gogp_optimize(gogp_handle* h, const gogp_opt_settings* settings, double* log_theta,
