@@ -13,6 +13,8 @@
 // thread).  Both operands are row-major with k contiguous ("NT"), staged as
 // [row][k] with a row pitch of 20 doubles: a half-warp's fragment read touches
 // rows r..r+3 x k..k+3 -> word offsets (20r + k)*2, all 32 banks distinct.
+#include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 
@@ -29,13 +31,13 @@ template <int WM, int WN, int STAGES, int MINB>
 void launch_cfg(const GemmArgs& g0, int64_t m, int64_t n, cudaStream_t s) {
     constexpr int BM = 64 * WM, BN = 32 * WN;
     constexpr size_t SMEM = (size_t)STAGES * (BM + BN) * PITCH * sizeof(double);
-    static bool configured[64] = {false};  // the attribute is per device
+    static std::atomic<bool> configured[64];  // the attribute is per device; handles on other threads may race here
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
+    if (!configured[dev & 63].load(std::memory_order_acquire)) {
         cudaFuncSetAttribute(dgemm_nt_kernel<WM, WN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SMEM);
-        configured[dev & 63] = true;
+        configured[dev & 63].store(true, std::memory_order_release);
     }
     GemmArgs g = g0;
     g.tm = (int)(m / BM);
@@ -86,17 +88,21 @@ static int g_gemm_cfg = -1;  // 0: 128x128 1 CTA/SM, 1: 128x64 2 CTAs/SM, 2: TMA
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
 void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
-                     int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s) {
+                     int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s,
+                     const GemmMask* mask) {
     static int64_t tma_min_k = 0;
-    if (g_gemm_cfg < 0) {
-        const char* e = getenv("GOGP_GEMM_CFG");
-        g_gemm_cfg = e ? atoi(e) : 2;
+    static std::once_flag knobs;  // handles on different host threads (one per GPU) come through here concurrently
+    std::call_once(knobs, [] {
         const char* mk = getenv("GOGP_TMA_MIN_K");
         tma_min_k = mk ? atoll(mk) : 512;  // below it the 2-CTA cp.async shape has the lower per-tile latency
-    }
+        if (g_gemm_cfg < 0) {
+            const char* e = getenv("GOGP_GEMM_CFG");
+            g_gemm_cfg = e ? atoi(e) : 2;
+        }
+    });
     if (k <= 0) return;
     if (g_gemm_cfg == 2 && k >= tma_min_k &&
-        launch_dgemm_tma(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s))
+        launch_dgemm_tma(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s, mask))
         return;
     GemmArgs g;
     g.C = C;
@@ -111,6 +117,13 @@ void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const
     g.mode = mode;
     g.alpha = alpha;
     g.beta = beta;
+    if (mask && mask->tb > 0) {
+        g.mtb = mask->tb;
+        g.mr0 = mask->r0;
+        g.mpr = mask->pr;
+        g.mc0 = mask->c0;
+        g.mpc = mask->pc;
+    }
     // C aliasing A needs a CTA that owns entire rows of the (128-wide) block
     if (g_gemm_cfg == 0 || (mode & GEMM_INPLACE))  // (cfg 2 falls back to the 2-CTA shape below)
         launch_cfg<2, 4, 4, 1>(g, m, n, s);

@@ -19,6 +19,8 @@ struct GemmArgs {
     int k;        // elements
     int mode;
     double alpha, beta;
+    // block-cyclic tile mask (kernels.h GemmMask), in 128-row tiles per distribution block; mtb == 0: off
+    int mtb = 0, mr0 = 0, mpr = 1, mc0 = 0, mpc = 1;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -82,6 +84,13 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_nt_kernel(const Gemm
         const int gsz = (g.tm - first) < GROUP_M ? (g.tm - first) : GROUP_M;
         ti = first + rem % gsz;
         tj = rem / gsz;
+    }
+    if (g.mtb > 0) {
+        // tile of a block-cyclic local matrix that lies strictly above the global diagonal: nothing to do
+        constexpr int CPB = 128 / BN;  // column tiles per 128 columns (BM is always 128)
+        const int tbn = g.mtb * CPB;
+        const int I = g.mr0 + g.mpr * (ti / g.mtb), J = g.mc0 + g.mpc * (tj / tbn);
+        if (J > I || (J == I && (tj % tbn) * BN > (ti % g.mtb) * BM + BM - 1)) return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WN, wn = warp % WN;

@@ -14,6 +14,8 @@
 // for a half-warp (4 rows x 4 fk) that is 16 distinct 8-byte bank pairs: no conflicts.
 #include <cuda.h>
 
+#include <atomic>
+
 #include <cstdio>
 #include <cstdlib>
 
@@ -62,15 +64,16 @@ bool make_map(CUtensorMap* map, const double* ptr, int64_t ld, int64_t rows, int
 // Returns false when the TMA path cannot be used (no driver entry point / encode failure):
 // the caller then launches the cp.async kernel.
 bool launch_dgemm_tma(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
-                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s) {
+                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s,
+                      const GemmMask* mask) {
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, A, lda, m, k) || !make_map(&mapB, B, ldb, n, k)) return false;
-    static bool configured[64] = {false};
+    static std::atomic<bool> configured[64];  // the attribute is per device; handles on other threads may race here
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
+    if (!configured[dev & 63].load(std::memory_order_acquire)) {
         cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        configured[dev & 63] = true;
+        configured[dev & 63].store(true, std::memory_order_release);
     }
     TmaArgs g;
     g.C = C;
@@ -82,6 +85,13 @@ bool launch_dgemm_tma(double* C, int64_t ldc, const double* A, int64_t lda, cons
     g.mode = mode;
     g.alpha = alpha;
     g.beta = beta;
+    if (mask && mask->tb > 0) {
+        g.mtb = mask->tb;
+        g.mr0 = mask->r0;
+        g.mpr = mask->pr;
+        g.mc0 = mask->c0;
+        g.mpc = mask->pc;
+    }
     const int ntiles = (mode & GEMM_LOWER) ? g.tm * (g.tm + 1) / 2 : g.tm * g.tn;
     if (ntiles <= 0) return true;
     dgemm_tma_kernel<<<ntiles, THREADS, SMEM_BYTES, s>>>(mapA, mapB, g);

@@ -20,6 +20,8 @@ struct TmaArgs {
     int k;
     int mode;
     double alpha, beta;
+    // block-cyclic tile mask (kernels.h GemmMask); mtb == 0: off
+    int mtb = 0, mr0 = 0, mpr = 1, mc0 = 0, mpc = 1;
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -127,6 +129,11 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int gsz = (g.tm - first) < GROUP_M ? (g.tm - first) : GROUP_M;
         ti = first + rem % gsz;
         tj = rem / gsz;
+    }
+    if (g.mtb > 0) {
+        // tile of a block-cyclic local matrix that lies strictly above the global diagonal: nothing to do
+        const int I = g.mr0 + g.mpr * (ti / g.mtb), J = g.mc0 + g.mpc * (tj / g.mtb);
+        if (J > I || (J == I && tj % g.mtb > ti % g.mtb)) return;
     }
     const int row0 = ti * BM, col0 = tj * BN;
     const int k_lo = (g.mode & GEMM_KTRI) ? ti * BM : 0;

@@ -58,12 +58,22 @@ enum GemmMode : int {
     GEMM_DIAG_OUT = 4,  // diagonal tiles go to cdiag ([T][128][128]) instead of C
     GEMM_INPLACE = 8,   // C aliases A (n == 128): one CTA must own entire rows of the block
 };
+// Block-cyclic tile mask (grid.hpp: C is a window of one rank's local matrix of a Pr x Pc block-cyclic
+// distribution with tb x tb tiles per distribution block).  Tile (ti, tj) of C belongs to global block
+// (I, J) = (r0 + pr * (ti / tb), c0 + pc * (tj / tb)); it is computed only when it meets the lower triangle of
+// the GLOBAL matrix: J < I, or J == I and the tile is on or below the block's diagonal.  tb == 0: no mask.
+struct GemmMask {
+    int tb = 0;
+    int r0 = 0, pr = 1, c0 = 0, pc = 1;
+};
 // C[i][j] = beta*C[i][j] + alpha * sum_k A[i][k] B[j][k]; all of m, n, k multiples of 128.
 void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
-                     int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s);
+                     int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s,
+                     const GemmMask* mask = nullptr);
 // TMA + mbarrier warp-specialised variant (dgemm_tma.cu); false: not available, use launch_dgemm_nt's kernels
 bool launch_dgemm_tma(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m,
-                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s);
+                      int64_t n, int64_t k, double alpha, double beta, int mode, double* cdiag, cudaStream_t s,
+                      const GemmMask* mask = nullptr);
 void set_gemm_config(int cfg);  // 0: 128x128 tiles, 1 CTA/SM; 1: 128x64 tiles, 2 CTAs/SM
 // register-only issue-rate microbenchmarks: which = 0 DMMA m8n8k4, 1 DFMA
 int fp64_peak_variants();
