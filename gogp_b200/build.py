@@ -16,9 +16,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libgogp_b200.so")
 
-CU_SOURCES = ["capi.cu", "cov.cu", "dgemm.cu", "dgemm_tma.cu", "leaf.cu"]
+CU_SOURCES = ["capi.cu", "cov.cu", "dgemm.cu", "dgemm_tma.cu", "leaf.cu", "grid.cu"]
 CC_SOURCES = ["program.cc"]
-HEADERS = ["program.h", "kexpr.cuh", "kernels.h", "blocked.hpp", "optimize.hpp", "leaf_kernels.cuh", "cov_kernels.cuh", "dgemm_kernels.cuh", "dgemm_tma_kernel.cuh", os.path.join("..", "..", "include", "gogp_b200.h")]
+HEADERS = ["program.h", "kexpr.cuh", "kernels.h", "blocked.hpp", "grid.hpp", "optimize.hpp", "leaf_kernels.cuh", "cov_kernels.cuh", "dgemm_kernels.cuh", "dgemm_tma_kernel.cuh", os.path.join("..", "..", "include", "gogp_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -67,7 +67,8 @@ def build(force=False, verbose=False):
         for l in logs:
             sys.stderr.write(l)
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+        # libnccl is bound at run time (dlopen in grid.cu), never at load time: the single-GPU path needs no NCCL
+        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

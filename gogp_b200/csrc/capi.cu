@@ -28,21 +28,19 @@ inline int64_t pad_tile(int64_t n) { return n <= 0 ? 0 : ((n + TILE - 1) / TILE)
 
 // Diagonal blocks up to this size use the short-chain (right-looking / column-wise)
 // variants of blocked.hpp; above it the recursion keeps every GEMM's K large.
+// (function-local statics with an initialiser are initialised once, thread-safely: handles on different host
+// threads -- one per GPU -- read these concurrently)
+inline int64_t env_i64(const char* name, int64_t dflt) {
+    const char* e = getenv(name);
+    return e ? atoll(e) : dflt;
+}
 inline int64_t rl_max() {
-    static int64_t v = -1;
-    if (v < 0) {
-        const char* e = getenv("GOGP_RL_MAX");
-        v = e ? atoll(e) : 4096;  // measured on B200 at N = 32768: potrf 431 ms (0) -> 412 ms (4096)
-    }
+    static const int64_t v = env_i64("GOGP_RL_MAX", 4096);  // measured on B200 at N = 32768: potrf 431 ms (0) -> 412 ms (4096)
     return v;
 }
 // Diagonal blocks up to this size are inverted concurrently on side streams (0: depth-first, one stream).
 inline int64_t par_block() {
-    static int64_t v = -1;
-    if (v < 0) {
-        const char* e = getenv("GOGP_PAR_BLOCK");
-        v = e ? atoll(e) : 1024;  // measured at N = 32768: potri 720.8 ms (0) -> 689.0 ms (1024)
-    }
+    static const int64_t v = env_i64("GOGP_PAR_BLOCK", 1024);  // measured at N = 32768: potri 720.8 ms (0) -> 689.0 ms (1024)
     return v;
 }
 // Block-column widths of the nested look-ahead factorisation (Blocked::potrf_la), outermost first;
@@ -62,11 +60,7 @@ inline void la_blocks(int64_t (&nb)[3]) {
 }
 // The column-wise inverse measured slower than the recursion (potri 722 -> 728 ms at 2048): off by default.
 inline int64_t cols_max() {
-    static int64_t v = -1;
-    if (v < 0) {
-        const char* e = getenv("GOGP_COLS_MAX");
-        v = e ? atoll(e) : 0;
-    }
+    static const int64_t v = env_i64("GOGP_COLS_MAX", 0);
     return v;
 }
 
@@ -172,7 +166,7 @@ struct CudaBackend {
         if (la) la[l].below_pending = false;
     }
     void gemm(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m, int64_t n,
-              int64_t k, double alpha, double beta, int mode, double* cdiag) {
+              int64_t k, double alpha, double beta, int mode, double* cdiag, const GemmMask* mask = nullptr) {
         const bool p = prof && prof->on;
         if (p) cudaEventRecord(prof->next(), s);
         if ((mode & GEMM_INPLACE) && scratch && m >= kOutOfPlaceRows && scratch_row + m <= scratch_rows && n == TILE) {
@@ -185,7 +179,7 @@ struct CudaBackend {
             launch_copy_block(C, ldc, scr, TILE, m, TILE, s);
             ++*launches;
         } else {
-            launch_dgemm_nt(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s);
+            launch_dgemm_nt(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s, mask);
         }
         if (p) {
             cudaEventRecord(prof->next(), s);
@@ -925,7 +919,6 @@ gogp_status gogp_debug_leaf(gogp_handle* h, int variant, int iters, double* usec
     const int64_t ld = 4096;
     CK(cudaMalloc(&A, (size_t)TILE * ld * sizeof(double)));
     CK(cudaMalloc(&W, (size_t)TILE * TILE * sizeof(double)));
-    set_leaf_variant(variant);
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         float total = 0.f;
@@ -933,7 +926,7 @@ gogp_status gogp_debug_leaf(gogp_handle* h, int variant, int iters, double* usec
             launch_fill(A, TILE * ld, 0.01, h->stream);          // SPD tile: 0.01 everywhere ...
             launch_fill_diag(A, ld + 1, TILE, 2.0, h->stream);   // ... and 2 on the diagonal
             cudaEventRecord(h->ev[0], h->stream);
-            launch_potrf_leaf(A, ld, W, h->dInfo, 0, h->stream);
+            launch_potrf_leaf(A, ld, W, h->dInfo, 0, h->stream, variant);
             cudaEventRecord(h->ev[1], h->stream);
             cudaStreamSynchronize(h->stream);
             float ms = 0.f;
@@ -942,7 +935,6 @@ gogp_status gogp_debug_leaf(gogp_handle* h, int variant, int iters, double* usec
         }
         if (total < best) best = total;
     }
-    set_leaf_variant(-1);  // back to the default (GOGP_LEAF or the blocked kernel)
     cudaFree(A);
     cudaFree(W);
     CK(cudaGetLastError());
@@ -956,15 +948,13 @@ gogp_status gogp_debug_leaf_run(gogp_handle* h, int variant, const double* A, do
     double* d = nullptr;
     const size_t bytes = (size_t)TILE * TILE * sizeof(double);
     CK(cudaMalloc(&d, 2 * bytes));
-    set_leaf_variant(variant);
     cudaMemsetAsync(h->dInfo, 0, sizeof(int), h->stream);
     cudaMemcpyAsync(d, A, bytes, cudaMemcpyHostToDevice, h->stream);
-    launch_potrf_leaf(d, TILE, d + TILE * TILE, h->dInfo, 0, h->stream);
+    launch_potrf_leaf(d, TILE, d + TILE * TILE, h->dInfo, 0, h->stream, variant);
     cudaMemcpyAsync(L, d, bytes, cudaMemcpyDeviceToHost, h->stream);
     cudaMemcpyAsync(W, d + TILE * TILE, bytes, cudaMemcpyDeviceToHost, h->stream);
     cudaMemcpyAsync(info, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    set_leaf_variant(-1);  // back to the default (GOGP_LEAF or the blocked kernel)
     cudaFree(d);
     ++h->launches;
     if (e != cudaSuccess) return fail(h, GOGP_CUDA_ERROR, cudaGetErrorString(e));
@@ -1107,6 +1097,30 @@ gogp_status gogp_dev_gemm(gogp_handle* h, double* C, int64_t ldc, const double* 
     be.gemm(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, lower ? GEMM_LOWER : GEMM_FULL, nullptr);
     CK(cudaGetLastError());
     return GOGP_OK;
+}
+
+gogp_status gogp_dev_gemm_bc(gogp_handle* h, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
+                             int64_t ldb, int64_t m, int64_t n, int64_t k, double alpha, double beta, int tb, int r0,
+                             int pr, int c0, int pc, int ktri, void* stream) {
+    if (!h || !C || !A || !B || m <= 0 || n <= 0 || k <= 0 || m % TILE || n % TILE || k % TILE) return GOGP_BAD_ARGUMENT;
+    if (tb < 0 || pr < 1 || pc < 1 || r0 < 0 || c0 < 0) return fail(h, GOGP_BAD_ARGUMENT, "bad block-cyclic mask");
+    CK(cudaSetDevice(h->dev));
+    CudaBackend be{pick_stream(h, stream), h->dInfo, &h->launches, &h->prof, nullptr, 0};
+    GemmMask mk;
+    mk.tb = tb;
+    mk.r0 = r0;
+    mk.pr = pr;
+    mk.c0 = c0;
+    mk.pc = pc;
+    be.gemm(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, ktri ? GEMM_KTRI : GEMM_FULL, nullptr, tb > 0 ? &mk : nullptr);
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_reserve(gogp_handle* h, int64_t rows) {
+    if (!h || rows < 0) return GOGP_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->dev));
+    return ensure_scratch(h, pad_tile(rows));
 }
 
 gogp_status gogp_dev_sumlogdiag(gogp_handle* h, const double* L, int64_t ld, int64_t nvalid, double* out,

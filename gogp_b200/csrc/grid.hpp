@@ -48,6 +48,8 @@ struct BcMask {
     int tb, r0, pr, c0, pc;
 };
 
+enum GridGemmFlags : int { GF_KTRI = 1 };  // A is upper triangular w.r.t. its own origin: k starts at the row tile
+
 enum GridPhase : int {
     GP_BUILD = 0,
     GP_FACTOR = 1,
@@ -215,10 +217,16 @@ struct BlockCyclic {
         for (int j = j0; j < j1; ++j) be.copy2d(cblk(g, j), NB, pblk(g, gcol(j)), NB, NB, NB, GQ_MAIN);
     }
 
+    // Queues.  The priority queue carries the chain of one block column (diagonal factor, panel solve, collectives,
+    // look-ahead update of block column k+1); the side queue carries the bulk of every trailing update, split so
+    // that the NEXT look-ahead column is updated first (event e1) and the rest after it (event done[g]).  The
+    // chain of step k+1 therefore overlaps the bulk of step k and waits only for e1; the two panel generations
+    // are recycled behind done[g].
     void factor() {
         cur_phase = GP_FACTOR;
         be.zero(scal, NSCAL, GQ_MAIN);
-        int prev_done = -1;
+        be.info_reset(GQ_MAIN);
+        int done[2] = {-1, -1}, e1_prev = -1;
         factor_diag(0);
         for (int k = 0; k + 1 < nb; ++k) {
             const int g = k & 1, kc = k % Pc;
@@ -228,47 +236,55 @@ struct BlockCyclic {
             comm_end();
             // panel solve A_Ik <- A_Ik L_kk^-T on process column kc: every source solves its own rows BEFORE any
             // broadcast is queued, so the Pr solves run concurrently
-            if (kc == myc) {
-                const int first = count_below(k + 1, myr, Pr), cnt = nr - first;
-                if (cnt > 0) {
-                    double* sub = blk(first, lcol(k));
-                    be.trsm(sub, ld, (int64_t)cnt * NB, lkk(), NB, NB, wkk(), GQ_MAIN);
-                    be.copy2d(myrows(g, first), NB, sub, ld, (int64_t)cnt * NB, NB, GQ_MAIN);
-                }
-            }
+            const int ir0 = count_below(k + 1, myr, Pr), jc0 = count_below(k + 1, myc, Pc);
+            const int mrows = nr - ir0, ncols = nc - jc0;
+            if (kc == myc && mrows > 0) be.trsm(blk(ir0, lcol(k)), ld, (int64_t)mrows * NB, lkk(), NB, NB, wkk(), GQ_MAIN);
+            if (done[g] >= 0) be.wait(GQ_MAIN, done[g]);  // the bulk of step k-2 read this panel generation
+            if (kc == myc && mrows > 0)
+                be.copy2d(myrows(g, ir0), NB, blk(ir0, lcol(k)), ld, (int64_t)mrows * NB, NB, GQ_MAIN);
             comm_begin();
             for (int rr = 0; rr < Pr; ++rr) {
                 const int first = count_below(k + 1, rr, Pr), cnt = rows_of(rr) - first;
                 if (cnt > 0) be.bcast(panel[g] + (prow_off[rr] + first) * bsz, (int64_t)cnt * bsz, rr * Pc + kc, GQ_MAIN);
             }
             comm_end();
-            const int ir0 = count_below(k + 1, myr, Pr), jc0 = count_below(k + 1, myc, Pc);
-            const int mrows = nr - ir0, ncols = nc - jc0;
             gather(g, jc0, nc);
-            // the previous step's bulk update (side queue) wrote the blocks the look-ahead touches
-            if (prev_done >= 0) be.wait(GQ_MAIN, prev_done);
+            const int fork = be.record(GQ_MAIN);
+            // step k-1's bulk updated block column k+1 first: that is all the look-ahead depends on
+            if (e1_prev >= 0) be.wait(GQ_MAIN, e1_prev);
+            e1_prev = -1;
             if (mrows > 0 && ncols > 0) {
                 const double* A = myrows(g, ir0);
                 int first = 0;
                 if (gcol(jc0) == k + 1) {
-                    // look-ahead: block column k+1 first, on the priority queue -- the next step's diagonal
+                    // look-ahead: block column k+1 on the priority queue -- the next step's diagonal
                     // factorisation, panel solve and broadcasts depend on nothing else
                     const BcMask m = mask_at(ir0, jc0);
                     be.gemm(blk(ir0, jc0), ld, A, NB, cblk(g, jc0), NB, (int64_t)mrows * NB, NB, NB, -1.0, 1.0, &m,
-                            GQ_MAIN);
+                            0, GQ_MAIN);
                     first = 1;
                 }
                 if (ncols > first) {
-                    be.wait(GQ_SIDE, be.record(GQ_MAIN));
-                    const BcMask m = mask_at(ir0, jc0 + first);
-                    be.gemm(blk(ir0, jc0 + first), ld, A, NB, cblk(g, jc0 + first), NB, (int64_t)mrows * NB,
-                            (int64_t)(ncols - first) * NB, NB, -1.0, 1.0, &m, GQ_SIDE);
-                    prev_done = be.record(GQ_SIDE);
+                    be.wait(GQ_SIDE, fork);
+                    const int j1 = jc0 + first, w1 = gcol(j1) == k + 2 ? 1 : 0;
+                    if (w1) {
+                        const BcMask m = mask_at(ir0, j1);
+                        be.gemm(blk(ir0, j1), ld, A, NB, cblk(g, j1), NB, (int64_t)mrows * NB, NB, NB, -1.0, 1.0, &m,
+                                0, GQ_SIDE);
+                    }
+                    e1_prev = be.record(GQ_SIDE);
+                    if (ncols - first - w1 > 0) {
+                        const BcMask m = mask_at(ir0, j1 + w1);
+                        be.gemm(blk(ir0, j1 + w1), ld, A, NB, cblk(g, j1 + w1), NB, (int64_t)mrows * NB,
+                                (int64_t)(ncols - first - w1) * NB, NB, -1.0, 1.0, &m, 0, GQ_SIDE);
+                    }
+                    done[g] = be.record(GQ_SIDE);
                 }
             }
             factor_diag(k + 1);
         }
-        if (prev_done >= 0) be.wait(GQ_MAIN, prev_done);
+        for (int g = 0; g < 2; ++g)
+            if (done[g] >= 0) be.wait(GQ_MAIN, done[g]);
         factored = true;
         have_kinv = false;
     }
@@ -328,7 +344,7 @@ struct BlockCyclic {
         be.zero(vdiag, (int64_t)(ndiag > 0 ? ndiag : 1) * bsz, GQ_MAIN);
         stage_diag(0);
         if (rank == owner(0, 0)) be.trtri_t(lkk(), NB, NB, wkk(), vd(0), GQ_MAIN);
-        int prev_done = -1;
+        int done[2] = {-1, -1}, e1_prev = -1;  // as in factor()
         for (int k = 0; k < nb; ++k) {
             const int g = k & 1, kc = k % Pc;
             if (k + 1 < nb) {
@@ -340,6 +356,7 @@ struct BlockCyclic {
                 comm_end();
                 if (rank == owner(k + 1, k + 1)) be.trtri_t(lkk(), NB, NB, wkk(), vd(k + 1), GQ_MAIN);
             }
+            if (done[g] >= 0) be.wait(GQ_MAIN, done[g]);  // the bulk of step k-2 read this panel generation
             // panel k = [V_ck (c <= k) ; L_ik (i > k)], from process column kc
             if (kc == myc && nr > 0) {
                 be.copy2d(myrows(g, 0), NB, blk(0, lcol(k)), ld, (int64_t)nr * NB, NB, GQ_MAIN);
@@ -351,7 +368,9 @@ struct BlockCyclic {
                     be.bcast(panel[g] + prow_off[rr] * bsz, (int64_t)rows_of(rr) * bsz, rr * Pc + kc, GQ_MAIN);
             comm_end();
             gather(g, 0, nc);
-            if (prev_done >= 0) be.wait(GQ_MAIN, prev_done);
+            const int fork = be.record(GQ_MAIN);
+            if (e1_prev >= 0) be.wait(GQ_MAIN, e1_prev);  // step k-1's bulk updated block column k+1 first
+            e1_prev = -1;
             const int nrk = count_below(k + 1, myr, Pr);  // my block rows <= k
             const int nck = count_below(k + 1, myc, Pc);  // my block columns <= k
             const double* A = myrows(g, 0);
@@ -360,35 +379,49 @@ struct BlockCyclic {
                 // look-ahead: finish block column k+1 of V (last update, then the solve with L_{k+1,k+1})
                 if (nrk > 0) {
                     be.gemm(blk(0, nck), ld, A, NB, cblk(g, nck), NB, (int64_t)nrk * NB, NB, NB, -1.0, 1.0, nullptr,
-                            GQ_MAIN);
+                            0, GQ_MAIN);
                     be.trsm(blk(0, nck), ld, (int64_t)nrk * NB, lkk(), NB, NB, wkk(), GQ_MAIN);
                 }
                 first = 1;
             }
             if (nrk == 0) continue;
-            be.wait(GQ_SIDE, be.record(GQ_MAIN));
-            // V_ci -= V_ck L_ik^T for my blocks c <= k < i beyond the look-ahead column
-            if (nc - nck - first > 0)
-                be.gemm(blk(0, nck + first), ld, A, NB, cblk(g, nck + first), NB, (int64_t)nrk * NB,
-                        (int64_t)(nc - nck - first) * NB, NB, -1.0, 1.0, nullptr, GQ_SIDE);
+            be.wait(GQ_SIDE, fork);
+            // V_ci -= V_ck L_ik^T for my blocks c <= k < i beyond the look-ahead column; the next look-ahead
+            // column (k+2) first
+            const int j1 = nck + first, w1 = (j1 < nc && gcol(j1) == k + 2) ? 1 : 0;
+            if (w1)
+                be.gemm(blk(0, j1), ld, A, NB, cblk(g, j1), NB, (int64_t)nrk * NB, NB, NB, -1.0, 1.0, nullptr, 0, GQ_SIDE);
+            e1_prev = be.record(GQ_SIDE);
+            const bool own_k = k % Pr == myr;  // my last block row <= k is row k itself: its A operand is V_kk,
+                                               // upper triangular -> triangular k range, half the flops
+            if (nc - j1 - w1 > 0) {
+                const int full = own_k ? nrk - 1 : nrk;
+                if (full > 0)
+                    be.gemm(blk(0, j1 + w1), ld, A, NB, cblk(g, j1 + w1), NB, (int64_t)full * NB,
+                            (int64_t)(nc - j1 - w1) * NB, NB, -1.0, 1.0, nullptr, 0, GQ_SIDE);
+                if (own_k)
+                    be.gemm(blk(nrk - 1, j1 + w1), ld, myrows(g, nrk - 1), NB, cblk(g, j1 + w1), NB, NB,
+                            (int64_t)(nc - j1 - w1) * NB, NB, -1.0, 1.0, nullptr, GF_KTRI, GQ_SIDE);
+            }
             // K^-1_ij += V_ik V_jk^T for my blocks j <= i <= k; block row k is touched for the first time
             if (nck > 0) {
                 int nrows = nrk;
-                if (k % Pr == myr) {
+                if (own_k) {
                     const BcMask m = mask_at(nrk - 1, 0);
                     be.gemm(blk(nrk - 1, 0), ld, myrows(g, nrk - 1), NB, cblk(g, 0), NB, NB, (int64_t)nck * NB, NB, 1.0,
-                            0.0, &m, GQ_SIDE);
+                            0.0, &m, GF_KTRI, GQ_SIDE);
                     nrows = nrk - 1;
                 }
                 if (nrows > 0) {
                     const BcMask m = mask_at(0, 0);
                     be.gemm(blk(0, 0), ld, A, NB, cblk(g, 0), NB, (int64_t)nrows * NB, (int64_t)nck * NB, NB, 1.0, 1.0,
-                            &m, GQ_SIDE);
+                            &m, 0, GQ_SIDE);
                 }
             }
-            prev_done = be.record(GQ_SIDE);
+            done[g] = be.record(GQ_SIDE);
         }
-        if (prev_done >= 0) be.wait(GQ_MAIN, prev_done);
+        for (int g = 0; g < 2; ++g)
+            if (done[g] >= 0) be.wait(GQ_MAIN, done[g]);
         factored = false;  // L has been overwritten
         have_kinv = true;
     }

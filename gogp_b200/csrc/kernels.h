@@ -84,8 +84,8 @@ double fp64_peak_flops_per_launch(int which, int variant, int iters, int nsm);
 // Cholesky of the 128x128 diagonal tile at A (ld), in place (lower; upper zeroed),
 // and its inverse into winv (128x128 row-major lower).  info: 0 or 1-based index
 // of the first non-positive pivot (global index = base + local).
-void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s);
-void set_leaf_variant(int v);  // timing aid, see leaf.cu
+// variant: -1 the process default (GOGP_LEAF, else the shipped blocked kernel); 0/1/2 select a kernel for timing runs.
+void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s, int variant = -1);
 // dst tile (ld) = winv^T (upper triangular, strictly-lower zeroed).
 void launch_trtri_leaf(const double* winv, double* dst, int64_t ld, cudaStream_t s);
 // Blocked triangular solves with the tile inverses.  fwd: out = L^-1 rhs; bwd: out = L^-T rhs.

@@ -2,8 +2,10 @@
 // Cholesky + inverse, blocked triangular solves for alpha = K^-1 y
 // (gp/gp.go:232-236), log-determinant and y.alpha (gp/gp.go:250-251), and small
 // reductions used by Produce (gp/gp.go:335-357).
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "kernels.h"
 
@@ -314,25 +316,27 @@ void launch_fill_pattern(double* v, int64_t n, cudaStream_t s) {
     if (n > 0) fill_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(v, n, 0.0, 1);
 }
 
-static int g_leaf_variant = -1;  // 0: blocked kernel (shipped), 1: first version (Crout, one barrier per column),
-                                 // 2: blocked kernel with the shared-memory column broadcast (timing candidate)
-void set_leaf_variant(int v) { g_leaf_variant = v; }
-
-void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s) {
-    if (g_leaf_variant < 0) {
+// variant 0: blocked kernel (shipped), 1: first version (Crout, one barrier per column), 2: blocked kernel with
+// the shared-memory column broadcast (timing candidate); -1: the process default (GOGP_LEAF, else 0).  The variant
+// is a launch argument, not a global: handles on other host threads are not affected by a timing run.
+void launch_potrf_leaf(double* A, int64_t ld, double* winv, int* info, int base, cudaStream_t s, int variant) {
+    static int default_variant = 0;
+    static std::once_flag knob;
+    std::call_once(knob, [] {
         const char* e = getenv("GOGP_LEAF");
-        g_leaf_variant = e ? atoi(e) : 0;
-    }
+        default_variant = e ? atoi(e) : 0;
+    });
+    const int g_leaf_variant = variant >= 0 ? variant : default_variant;
     const size_t smem_crout = (size_t)TILE * LP * sizeof(double);
     const size_t smem = ((size_t)TILE * LP + 32 * MP + 64) * sizeof(double);
-    static bool configured[64] = {false};  // the attribute is per device
+    static std::atomic<bool> configured[64];  // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
+    if (!configured[dev & 63].load(std::memory_order_acquire)) {
         cudaFuncSetAttribute(potrf_leaf_crout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_crout);
         cudaFuncSetAttribute(potrf_leaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(potrf_leaf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[dev & 63] = true;
+        configured[dev & 63].store(true, std::memory_order_release);
     }
     if (g_leaf_variant == 1)
         potrf_leaf_crout_kernel<<<1, 512, smem_crout, s>>>(A, ld, winv, info, base);
@@ -350,20 +354,21 @@ void launch_trsv_lower(const double* L, int64_t ld, const double* winv, double* 
                        bool transposed, cudaStream_t s, int64_t* launches, unsigned* sync) {
     // rhs may be consumed (the step kernels use it as the running right-hand side); out must not alias it.
     const int T = (int)(Npad / TILE);
-    static int chain = -1;  // 1: one launch per direction (default), 0: one launch per block (GOGP_TRSV=0)
-    if (chain < 0) {
+    static int chain = 1;  // 1: one launch per direction (default), 0: one launch per block (GOGP_TRSV=0)
+    static std::once_flag knob;
+    std::call_once(knob, [] {
         const char* e = getenv("GOGP_TRSV");
         chain = e ? atoi(e) : 1;
-    }
+    });
     if (chain && sync && T > 1) {
         const size_t smem = (size_t)TILE * WP * sizeof(double);
-        static bool configured[64] = {false};
+        static std::atomic<bool> configured[64];
         int dev = 0;
         cudaGetDevice(&dev);
-        if (!configured[dev & 63]) {
+        if (!configured[dev & 63].load(std::memory_order_acquire)) {
             cudaFuncSetAttribute(trsv_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(trsv_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured[dev & 63] = true;
+            configured[dev & 63].store(true, std::memory_order_release);
         }
         cudaMemsetAsync(sync, 0, (size_t)(T + 1) * sizeof(unsigned), s);
         if (!transposed)

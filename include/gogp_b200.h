@@ -194,6 +194,18 @@ gogp_status gogp_dev_trsm(gogp_handle* h, double* B, int64_t ldb, int64_t m, con
 gogp_status gogp_dev_gemm(gogp_handle* h, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
                           int64_t ldb, int64_t m, int64_t n, int64_t k, double alpha, double beta, int lower,
                           void* stream);
+/* The same GEMM on a window of one rank's local matrix of a pr x pc block-cyclic distribution with tb x tb tiles
+ * per distribution block: tile (ti, tj) of C belongs to global block (r0 + pr (ti / tb), c0 + pc (tj / tb)) and is
+ * computed only where it meets the lower triangle of the global matrix (tb == 0: no mask).  One launch per
+ * trailing update instead of one per owned block row (gogp_b200/csrc/grid.hpp).  ktri != 0: A is upper
+ * triangular with respect to its own origin (a diagonal block of L^-T), the k range of row tile ti starts at
+ * ti * 128. */
+gogp_status gogp_dev_gemm_bc(gogp_handle* h, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
+                             int64_t ldb, int64_t m, int64_t n, int64_t k, double alpha, double beta, int tb, int r0,
+                             int pr, int c0, int pc, int ktri, void* stream);
+/* Pre-allocate the scratch gogp_dev_trsm needs for right-hand sides of up to `rows` rows, so that no allocation
+ * happens between collectives. */
+gogp_status gogp_dev_reserve(gogp_handle* h, int64_t rows);
 /* out[0] = sum_{i < nvalid} log L_ii of a factored block. */
 gogp_status gogp_dev_sumlogdiag(gogp_handle* h, const double* L, int64_t ld, int64_t nvalid, double* out,
                                 void* stream);
@@ -250,6 +262,66 @@ gogp_status gogp_dev_trace_block(gogp_handle* h, const double* theta_simil, cons
 /* Host arithmetic on the (input-independent) noise program: variance and d variance / d log theta_n
  * at natural-scale theta_noise; the noise gradient is 0.5 tr(W) dlog[q] (gp/gp.go:133-150). */
 gogp_status gogp_noise_eval(gogp_handle* h, const double* theta_noise, double* variance, double* dlog);
+
+/* ---- gp.GP across the GPUs of one box: 2D block-cyclic K, NCCL inside the library ---------------------------
+ * (SURVEY.md section 8e / 8b `gogp_create_grid`; BASELINE configs[4], N = 131072.)  The covariance matrix no longer
+ * fits one GPU: K is cut into block x block pieces dealt round-robin to a pr x pc process grid, every rank builds
+ * its own pieces from the replicated inputs, and Observe / Gradient (gp/gp.go:374-413, 418-499) run as a
+ * right-looking block Cholesky plus one fused pass for V = L^-T and K^-1 = V V^T, with NCCL broadcasts of the
+ * panels over NVLink (gogp_b200/csrc/grid.hpp, grid.cu).  libnccl.so.2 is bound at the first grid call (dlopen:
+ * the copy already loaded in the process, e.g. PyTorch's, else the system one); a library without NCCL still
+ * serves every single-GPU entry point, and a grid call then fails with GOGP_NCCL_ERROR.
+ *
+ * Two ways to form the grid:
+ *   - gogp_create_grid: ONE process drives all GPUs (the Go host of north_star: one gp.GP value, one cgo call
+ *     per Observe).  The library runs one host thread per device for the duration of each call.
+ *   - gogp_grid_unique_id + gogp_grid_create_rank: SPMD, one process (or thread) per GPU, e.g. under
+ *     torchrun; every rank makes the same calls with the same arguments, like MPI.  The 128-byte id is created
+ *     by one rank and distributed by the host (any channel).
+ * Results (LML, gradient) are replicated: every rank returns the same numbers.  pr * pc must equal the number of
+ * ranks (pr = pc = 0: the default grid, pr >= pc, powers of two); block is a multiple of 128 (0: 2048).
+ * Hyper-parameters-only mode (gp.X, gp.Y assigned as fields, tutorial/tutorial.go:114-115); the with_obs input
+ * gradient and Produce stay single-GPU (gogp_observe / gogp_produce). */
+typedef struct gogp_grid gogp_grid;
+#define GOGP_GRID_ID_BYTES 128
+enum {
+    GOGP_GRID_BUILD = 0,  /* covariance build of the owned blocks */
+    GOGP_GRID_FACTOR = 1, /* block-cyclic Cholesky */
+    GOGP_GRID_SOLVE = 2,  /* z = L^-1 y, log det, LML */
+    GOGP_GRID_SWEEP = 3,  /* V = L^-T and K^-1 = V V^T, one pass */
+    GOGP_GRID_ALPHA = 4,  /* alpha = V z */
+    GOGP_GRID_TRACE = 5,  /* fused gradient trace + all-reduce */
+    GOGP_GRID_NPHASE = 6
+};
+gogp_status gogp_create_grid(int ndim, const gogp_op* simil, int n_simil_ops, int ntheta_simil,
+                             const gogp_op* noise, int n_noise_ops, int ntheta_noise,
+                             const int* devices, int ndev, int pr, int pc, int64_t block, gogp_grid** out);
+gogp_status gogp_grid_unique_id(unsigned char id[GOGP_GRID_ID_BYTES]);
+gogp_status gogp_grid_create_rank(int ndim, const gogp_op* simil, int n_simil_ops, int ntheta_simil,
+                                  const gogp_op* noise, int n_noise_ops, int ntheta_noise,
+                                  int device, int rank, int world, int pr, int pc, int64_t block,
+                                  const unsigned char id[GOGP_GRID_ID_BYTES], gogp_grid** out);
+void gogp_grid_destroy(gogp_grid* g);
+/* gp.X, gp.Y (replicated on every rank); allocates the rank's share of K: about N^2 * 8 / (pr pc) bytes plus
+ * two panels of N * block * 8 bytes.  GOGP_OUT_OF_MEMORY when it does not fit. */
+gogp_status gogp_grid_set_data(gogp_grid* g, const double* X, const double* Y, int64_t N);
+/* gp.GP.Observe, hyper-parameters only: log marginal likelihood at log_theta (ntheta_simil + ntheta_noise). */
+gogp_status gogp_grid_observe(gogp_grid* g, const double* log_theta, double* lml);
+/* gp.GP.Gradient of the last gogp_grid_observe with respect to log_theta; len = ntheta_simil + ntheta_noise. */
+gogp_status gogp_grid_gradient(gogp_grid* g, double* grad, int64_t len);
+/* gp.GP.Absorb with the data of gogp_grid_set_data (natural-scale parameters) and gp.GP.LML. */
+gogp_status gogp_grid_absorb(gogp_grid* g, const double* theta_simil, const double* theta_noise);
+gogp_status gogp_grid_lml(gogp_grid* g, double* lml);
+/* alpha = K^-1 y (N values), available after gogp_grid_gradient. */
+gogp_status gogp_grid_get_alpha(gogp_grid* g, double* alpha, int64_t N);
+/* Device milliseconds per phase of the last Observe and Gradient (max over the ranks this process drives), and
+ * the part of each phase the priority stream spent inside NCCL calls (it includes waiting for peers). */
+gogp_status gogp_grid_phase_times(const gogp_grid* g, double* ms /* GOGP_GRID_NPHASE */,
+                                  double* comm_ms /* GOGP_GRID_NPHASE or NULL */);
+/* stats[0] bytes received through NCCL by the first local rank since creation, [1] kernels launched by it,
+ * [2] pr, [3] pc, [4] block, [5] bytes of device memory held by it, [6] NCCL version code. */
+gogp_status gogp_grid_stats(const gogp_grid* g, double* stats /* 8 */);
+const char* gogp_grid_last_error(const gogp_grid* g);
 
 /* Test/diagnostic access to device state: what = 0 K (before factorisation is
  * not kept; returns the factor buffer), 1 L, 2 K^-1 (after gogp_gradient).

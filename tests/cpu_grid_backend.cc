@@ -121,7 +121,7 @@ struct HostGridBackend {
         bl.trtri_t(out, 0, n);
     }
     void gemm(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t m, int64_t n,
-              int64_t k, double alpha, double beta, const BcMask* mk, int) {
+              int64_t k, double alpha, double beta, const BcMask* mk, int flags, int) {
         std::vector<double> tile(128 * 128);
         for (int64_t ti = 0; ti < m / 128; ++ti)
             for (int64_t tj = 0; tj < n / 128; ++tj) {
@@ -138,7 +138,7 @@ struct HostGridBackend {
                         const double* a = A + (ti * 128 + i) * lda;
                         const double* b = B + (tj * 128 + j) * ldb;
                         double s = 0.0;
-                        for (int64_t kk = 0; kk < k; ++kk) s += a[kk] * b[kk];
+                        for (int64_t kk = (flags & GF_KTRI) ? ti * 128 : 0; kk < k; ++kk) s += a[kk] * b[kk];
                         tile[i * 128 + j] = s;
                     }
                 for (int i = 0; i < 128; ++i)
@@ -200,6 +200,7 @@ struct HostGridBackend {
                 }
             }
     }
+    void info_reset(int) { info = 0; }
     void info_to(double* dst, int) { *dst = (double)info; }
     int info_host() { return info; }
 
