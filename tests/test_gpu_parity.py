@@ -364,8 +364,7 @@ def test_full_size_properties_n32768():
     single-GPU, block-cyclic with 2048-blocks) give the same LML, (iii) repeat evaluation is
     bit-identical, (iv) predictions at training inputs reproduce y within the noise level."""
     import bench
-    from gogp_b200 import GP, kernel as k
-    from gogp_b200.dist_chol import BlockCyclicCholesky, CudaBlocks
+    from gogp_b200 import GP, GridGP, kernel as k
     N, D = 32768, 8
     e = k.Param(0)
     for d in range(D):
@@ -394,16 +393,15 @@ def test_full_size_properties_n32768():
     g2 = g.Gradient()
     assert lml2 == lml and np.array_equal(g2, grad)
     g.close()
-    # (ii) the block-cyclic path on the same inputs
-    be = CudaBlocks(e, k.UniformNoise, D, 0)
-    be.set_inputs(X, 2048)
-    ch = BlockCyclicCholesky(be, N, 2048)
-    th = np.exp(t0)
-    ch.build(th[:D + 3], th[D + 3:])
-    ch.factor()
-    lml_bc = ch.solve_lml(y)
-    be.close()
+    # (ii) the block-cyclic path (gogp_grid_*, one rank, 2048-blocks: right-looking factorisation and the fused
+    # V / K^-1 sweep instead of the recursion) on the same inputs
+    gg = GridGP(NDim=D, Simil=e, Noise=k.UniformNoise, Devices=[0], Block=2048)
+    gg.X, gg.Y = X, y
+    lml_bc = gg.Observe(t0.copy())
+    grad_bc = gg.Gradient()
+    gg.close()
     assert abs(lml_bc - lml) <= 1e-11 * max(abs(lml), N), (lml_bc, lml)
+    assert np.max(np.abs(grad_bc - grad)) <= 1e-9 * max(1.0, np.max(np.abs(grad))), (grad_bc, grad)
 
 
 def test_produce_chunks_many_test_points():
