@@ -191,6 +191,10 @@ func (gp *GP) Absorb(x [][]float64, y []float64) error {
 		return err
 	}
 	xf := flatten(x, gp.NDim)
+	// the C-ABI takes one N for both buffers: a ragged x or len(x) != len(y) must not reach it
+	if len(xf) != len(y)*gp.NDim {
+		return errors.New("gp: len(x) != len(y) (or a row of x is not NDim long)")
+	}
 	gp.withObs, gp.n = false, len(y)
 	if st := C.gogp_absorb(h, dptr(gp.ThetaSimil), dptr(gp.ThetaNoise), dptr(xf), dptr(y), C.int64_t(len(y))); st != C.GOGP_OK {
 		return gp.fail(st)
@@ -215,6 +219,9 @@ func (gp *GP) Produce(x [][]float64) (mu, sigma []float64, err error) {
 		return nil, nil, err
 	}
 	zf := flatten(x, gp.NDim)
+	if len(zf) != len(x)*gp.NDim {
+		return nil, nil, errors.New("gp: a row of x is not NDim long")
+	}
 	mu = make([]float64, len(x))
 	sigma = make([]float64, len(x))
 	if st := C.gogp_produce(h, dptr(zf), C.int64_t(len(x)), dptr(mu), dptr(sigma)); st != C.GOGP_OK {
@@ -261,6 +268,9 @@ func (gp *GP) Observe(x []float64) float64 {
 		yf = gp.Y
 	} else {
 		xf, yf = flatten(gp.X, gp.NDim), gp.Y
+		if len(xf) != len(yf)*gp.NDim {
+			panic("len(gp.X) != len(gp.Y)")
+		}
 	}
 	if len(x) != 0 {
 		panic("len(x)")
@@ -294,6 +304,54 @@ func (gp *GP) Gradient() []float64 {
 	return grad
 }
 
+// Alpha is K^-1 y of the absorbed observations: the reference's exported gp.Alpha
+// (gp/gp.go:36), which a user may store.
+func (gp *GP) Alpha() []float64 {
+	a := make([]float64, gp.n)
+	if gp.h == nil || gp.n == 0 {
+		return a
+	}
+	if st := C.gogp_get_alpha(gp.h, dptr(a), C.int64_t(gp.n)); st != C.GOGP_OK {
+		panic(gp.fail(st))
+	}
+	return a
+}
+
+// L is the lower Cholesky factor of the covariance matrix, n x n row-major: the
+// reference's exported gp.L (gp/gp.go:35).
+func (gp *GP) L() []float64 {
+	l := make([]float64, gp.n*gp.n)
+	if gp.h == nil || gp.n == 0 {
+		return l
+	}
+	if st := C.gogp_get_factor(gp.h, dptr(l), C.int64_t(gp.n)); st != C.GOGP_OK {
+		panic(gp.fail(st))
+	}
+	return l
+}
+
+// Restore puts stored results back before Produce ("Produce works on stored
+// results", gp/gp.go:255-257): the parameters and inputs of the stored
+// factorisation with what Alpha() and L() returned.
+func (gp *GP) Restore(thetaSimil, thetaNoise []float64, x [][]float64, alpha, l []float64) error {
+	h, err := gp.handle()
+	if err != nil {
+		return err
+	}
+	xf := flatten(x, gp.NDim)
+	n := len(alpha)
+	if len(xf) != n*gp.NDim || len(l) != n*n || len(thetaSimil) != gp.Simil.NTheta() || len(thetaNoise) != gp.ntn() {
+		return errors.New("gp: state shapes do not agree")
+	}
+	gp.ThetaSimil = append([]float64(nil), thetaSimil...)
+	gp.ThetaNoise = append([]float64(nil), thetaNoise...)
+	gp.X, gp.withObs, gp.n = x, false, n
+	if st := C.gogp_set_state(h, dptr(gp.ThetaSimil), dptr(gp.ThetaNoise), dptr(xf), C.int64_t(n), dptr(alpha), dptr(l)); st != C.GOGP_OK {
+		return gp.fail(st)
+	}
+	return nil
+}
+
 // OptResult reports what Optimize did (gogp_opt_result).
 type OptResult struct {
 	Iters, Evals, Grads int
@@ -317,6 +375,9 @@ func (gp *GP) Optimize(x []float64, alg string, iters int, threshold, rate float
 		return OptResult{}, errors.New("len(x)")
 	}
 	xf := flatten(gp.X, gp.NDim)
+	if len(xf) != len(gp.Y)*gp.NDim {
+		return OptResult{}, errors.New("gp: len(gp.X) != len(gp.Y)")
+	}
 	if st := C.gogp_set_data(h, dptr(xf), dptr(gp.Y), C.int64_t(len(gp.Y))); st != C.GOGP_OK {
 		return OptResult{}, gp.fail(st)
 	}

@@ -24,7 +24,7 @@ PHASES = ("upload", "build", "potrf", "solve", "potri", "trace", "predict")
 # every symbol include/gogp_b200.h declares
 SYMBOLS = (
     "gogp_create", "gogp_destroy", "gogp_set_events", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_lml",
-    "gogp_produce", "gogp_optimize", "gogp_get_alpha", "gogp_get_factor", "gogp_last_error", "gogp_status_string",
+    "gogp_produce", "gogp_optimize", "gogp_get_alpha", "gogp_get_factor", "gogp_set_state", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
     "gogp_debug_gemm", "gogp_debug_leaf", "gogp_debug_leaf_run", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
     "gogp_dev_gemm", "gogp_dev_gemm_bc", "gogp_dev_reserve", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_dev_trtri_t", "gogp_dev_trace_block", "gogp_noise_eval", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
@@ -102,6 +102,8 @@ def lib():
     L.gogp_get_alpha.restype = C.c_int
     L.gogp_get_factor.argtypes = [H, dp, C.c_int64]
     L.gogp_get_factor.restype = C.c_int
+    L.gogp_set_state.argtypes = [H, dp, dp, dp, C.c_int64, dp, dp]
+    L.gogp_set_state.restype = C.c_int
     L.gogp_last_error.argtypes = [H]
     L.gogp_last_error.restype = C.c_char_p
     L.gogp_status_string.argtypes = [C.c_int]

@@ -232,8 +232,11 @@ struct gogp_handle {
     // evaluation memo: infer.FuncGrad evaluates Observe twice at the same
     // point (value, then value + gradient); the second call is answered from the cached factor
     bool memo_valid = false;
-    uint64_t memo_key = 0;
+    uint64_t memo_key = 0, memo_key2 = 0;  // two independent 64-bit digests of host-supplied X, Y
+    std::vector<double> memo_theta;        // the log parameters of the cached evaluation, compared exactly
     int64_t memo_hits = 0;
+    bool have_lml = false;                 // false after gogp_set_state: the stored state has no Y
+    double cond_bound = 0.0;               // lower bound of cond_2(K) of the last factorisation
     double lml = 0.0;
     std::string err;
     double phase_ms[GOGP_NPHASE] = {0};
@@ -341,6 +344,17 @@ inline uint64_t hash_bytes(uint64_t h, const void* p, size_t n) {
     return h;
 }
 
+inline uint64_t hash_bytes2(uint64_t h, const void* p, size_t n) {
+    // an independent digest (different multiplier, rotation instead of shift): both must collide for a stale hit
+    const uint64_t* w = static_cast<const uint64_t*>(p);
+    for (size_t i = 0; i < n / 8; ++i) {
+        h += w[i] * 0xD6E8FEB86659FD93ull;
+        h = (h << 31) | (h >> 33);
+        h *= 0xCA5A826395121157ull;
+    }
+    return h;
+}
+
 // Upload X (N x D) and Y (N); build the dimension-major copy.
 gogp_status upload_data(gogp_handle* h, const double* X, const double* Y, int64_t N) {
     if (N < 0) return fail(h, GOGP_BAD_ARGUMENT, "negative N");
@@ -372,6 +386,77 @@ void set_theta(gogp_handle* h, const double* ts, const double* tn) {
     h->noise_var = h->noise.eval_scalar(h->theta_n.data(), h->noise_dlog.data());
 }
 
+// gonum's Cholesky.SolveVecTo / SolveTo return a Condition error when the estimated condition number of K exceeds
+// 1e16 (mat.ConditionTolerance; the reference passes it on: gp/gp.go:233-236, 338-340).  Two stages:
+//   1. free: (max L_ii / min L_ii)^2 <= cond_2(K), from the log-determinant kernel;
+//   2. only when stage 1 exceeds kCondSuspect: Rayleigh quotients after a few power iterations on K = L L^T
+//      (two triangular mat-vecs) and on K^-1 (the two triangular solves), lambda_max(K) lambda_max(K^-1) -- both
+//      lower bounds, so a matrix is never flagged wrongly; gonum's estimate is of cond_1 >= cond_2, so a matrix
+//      with cond_2 in (1e16 / N, 1e16) may pass here and not there.
+constexpr double kCondTolerance = 1e16, kCondSuspect = 1e8;
+
+gogp_status cond_estimate(gogp_handle* h, double* cond) {
+    const int64_t N = h->N, Npad = h->Npad;
+    cudaStream_t s = h->stream;
+    double* v = h->dW;
+    double* t = h->dZ;
+    double* u = h->dGx;  // N * ndim >= N doubles, free outside the with_obs gradient
+    gogp_status st = ensure_pin(h, 8);
+    if (st != GOGP_OK) return st;
+    auto norm2 = [&](const double* x, double* out) -> gogp_status {
+        launch_row_reduce(x, Npad, 1, N, nullptr, h->dRed + 8, s);
+        CK(cudaMemcpyAsync(h->hPin + 4, h->dRed + 8, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        *out = h->hPin[4];
+        return GOGP_OK;
+    };
+    auto start = [&]() -> gogp_status {
+        CK(cudaMemsetAsync(v, 0, (size_t)Npad * sizeof(double), s));
+        launch_fill_pattern(v, N, s);  // the identity block of the padding is decoupled: zeros there stay zeros
+        double n2 = 0.0;
+        gogp_status e = norm2(v, &n2);
+        if (e != GOGP_OK) return e;
+        CK(cudaMemsetAsync(t, 0, (size_t)Npad * sizeof(double), s));
+        launch_axpy(t, v, 1.0 / std::sqrt(n2), N, s);
+        CK(cudaMemcpyAsync(v, t, (size_t)Npad * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        return GOGP_OK;
+    };
+    double lam_max = 0.0, lam_inv = 0.0;
+    for (int which = 0; which < 2; ++which) {
+        st = start();
+        if (st != GOGP_OK) return st;
+        double prev = 0.0;
+        for (int it = 0; it < 24; ++it) {
+            double q = 0.0, n2 = 0.0;
+            if (which == 0) {
+                launch_trmv_lower(h->dA, Npad, v, t, N, true, s);   // t = L^T v, |t|^2 = v^T K v
+                st = norm2(t, &q);
+                if (st != GOGP_OK) return st;
+                CK(cudaMemsetAsync(u, 0, (size_t)Npad * sizeof(double), s));
+                launch_trmv_lower(h->dA, Npad, t, u, N, false, s);  // u = K v
+            } else {
+                CK(cudaMemsetAsync(t, 0, (size_t)Npad * sizeof(double), s));
+                launch_trsv_lower(h->dA, Npad, h->dWinv, v, t, Npad, false, s, &h->launches, h->dSync);  // t = L^-1 v
+                st = norm2(t, &q);                                                                       // v^T K^-1 v
+                if (st != GOGP_OK) return st;
+                CK(cudaMemcpyAsync(v, t, (size_t)Npad * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                launch_trsv_lower(h->dA, Npad, h->dWinv, v, u, Npad, true, s, &h->launches, h->dSync);   // u = K^-1 v
+            }
+            h->launches += 3;
+            (which == 0 ? lam_max : lam_inv) = q > (which == 0 ? lam_max : lam_inv) ? q : (which == 0 ? lam_max : lam_inv);
+            st = norm2(u, &n2);
+            if (st != GOGP_OK) return st;
+            if (!(n2 > 0.0) || !std::isfinite(n2)) break;
+            CK(cudaMemsetAsync(v, 0, (size_t)Npad * sizeof(double), s));
+            launch_axpy(v, u, 1.0 / std::sqrt(n2), N, s);
+            if (it > 1 && std::fabs(q - prev) <= 1e-3 * q) break;
+            prev = q;
+        }
+    }
+    *cond = lam_max * lam_inv;
+    return GOGP_OK;
+}
+
 // absorb (gp/gp.go:89-239): build K, factor, alpha; then LML (gp/gp.go:244-253).
 gogp_status absorb(gogp_handle* h) {
     h->factored = false;
@@ -385,6 +470,7 @@ gogp_status absorb(gogp_handle* h) {
     if (h->N == 0) {
         h->lml = 0.0;
         h->factored = true;
+        h->have_lml = true;
         return GOGP_OK;
     }
     const int64_t N = h->N, Npad = h->Npad;
@@ -418,8 +504,8 @@ gogp_status absorb(gogp_handle* h) {
     CK(cudaEventRecord(h->ev[3], s));
     gogp_status st = ensure_pin(h, 8);
     if (st != GOGP_OK) return st;
-    CK(cudaMemcpyAsync(h->hPin, h->dRed, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->hPin + 2, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->hPin, h->dRed, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->hPin + 6, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     float ms = 0.f;
@@ -431,16 +517,35 @@ gogp_status absorb(gogp_handle* h) {
     h->phase_ms[GOGP_PHASE_SOLVE] = ms;
 
     int info = 0;
-    memcpy(&info, h->hPin + 2, sizeof(int));
+    memcpy(&info, h->hPin + 6, sizeof(int));
     if (info != 0) {
         char buf[160];
         snprintf(buf, sizeof buf, "Factorize: covariance matrix is not positive definite (pivot %d of %lld)", info,
                  (long long)N);
         return fail(h, GOGP_NOT_POSITIVE_DEFINITE, buf);
     }
-    const double sumlog = h->hPin[0], ydot = h->hPin[1];
+    const double sumlog = h->hPin[0], ydot = h->hPin[1], dmin = h->hPin[2], dmax = h->hPin[3];
     h->lml = -0.5 * (double)N * std::log(2 * M_PI) - 0.5 * (2.0 * sumlog) - 0.5 * ydot;
     h->factored = true;
+    h->have_lml = true;
+    // the state (L, alpha, LML) is complete, as in the reference, where the Condition error comes with the solution
+    h->cond_bound = dmin > 0.0 ? (dmax / dmin) * (dmax / dmin) : INFINITY;
+    if (h->cond_bound > kCondSuspect) {
+        double c2 = 0.0;
+        CK(cudaEventRecord(h->ev[2], s));
+        st = cond_estimate(h, &c2);
+        if (st != GOGP_OK) return st;
+        CK(cudaEventRecord(h->ev[3], s));
+        CK(cudaStreamSynchronize(s));
+        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+        h->phase_ms[GOGP_PHASE_SOLVE] += ms;
+        if (c2 > h->cond_bound) h->cond_bound = c2;
+        if (!(h->cond_bound <= kCondTolerance)) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "matrix singular or near-singular with condition number %.4e", h->cond_bound);
+            return fail(h, GOGP_ILL_CONDITIONED, buf);  // gonum's mat.Condition text
+        }
+    }
     return GOGP_OK;
 }
 
@@ -561,15 +666,21 @@ gogp_status gogp_observe(gogp_handle* h, const double* log_theta, int with_obs, 
     for (int i = 0; i < h->ntn; ++i) tn[i] = std::exp(log_theta[h->nts + i]);
     if (with_obs && N > 0 && (!X || !Y)) return fail(h, GOGP_BAD_ARGUMENT, "with_obs needs X and Y");
     // memo: same parameters on the same observations as the last successful evaluation
-    uint64_t key = 0x243F6A8885A308D3ull ^ (uint64_t)(with_obs != 0) ^ ((uint64_t)(X != nullptr) << 1);
-    key = hash_bytes(key, log_theta, (size_t)(h->nts + h->ntn) * 8);
+    // the parameters are compared exactly; host-supplied X, Y (which the library does not keep) by N and two
+    // independent 64-bit digests
+    const int P0 = h->nts + h->ntn;
+    uint64_t key = 0x243F6A8885A308D3ull ^ (uint64_t)(with_obs != 0) ^ ((uint64_t)(X != nullptr) << 1), key2 = ~key;
     if (X) {
         key = hash_bytes(key ^ (uint64_t)N, X, (size_t)N * h->ndim * 8);
         key = hash_bytes(key, Y, (size_t)N * 8);
+        key2 = hash_bytes2(key2 ^ (uint64_t)N, X, (size_t)N * h->ndim * 8);
+        key2 = hash_bytes2(key2, Y, (size_t)N * 8);
     }
     const bool same_data = X ? true : h->has_data;  // resident data: any gogp_set_data clears the memo
-    if (h->memo_valid && h->factored && same_data && key == h->memo_key && (with_obs != 0) == h->with_obs &&
-        (!X || N == h->N)) {
+    const bool same_theta = (int)h->memo_theta.size() == P0 &&
+                            (P0 == 0 || memcmp(h->memo_theta.data(), log_theta, (size_t)P0 * sizeof(double)) == 0);
+    if (h->memo_valid && h->factored && same_data && same_theta && key == h->memo_key && key2 == h->memo_key2 &&
+        (with_obs != 0) == h->with_obs && (!X || N == h->N)) {
         ++h->memo_hits;
         for (double& m : h->phase_ms) m = 0.0;
         *lml = h->lml;
@@ -585,6 +696,7 @@ gogp_status gogp_observe(gogp_handle* h, const double* log_theta, int with_obs, 
     CK(cudaEventRecord(h->ev[5], h->stream));
     h->with_obs = with_obs != 0;
     gogp_status st = absorb(h);
+    if (st == GOGP_ILL_CONDITIONED) *lml = h->lml;  // the value exists; the reference panics with the Condition error
     if (st != GOGP_OK) return st;
     if (h->N > 0) {  // events are complete: absorb synchronised the stream
         float ms = 0.f;
@@ -592,6 +704,8 @@ gogp_status gogp_observe(gogp_handle* h, const double* log_theta, int with_obs, 
         h->phase_ms[GOGP_PHASE_UPLOAD] = ms;
     }
     h->memo_key = key;
+    h->memo_key2 = key2;
+    h->memo_theta.assign(log_theta, log_theta + P0);
     h->memo_valid = true;
     *lml = h->lml;
     return GOGP_OK;
@@ -616,6 +730,7 @@ gogp_status gogp_absorb(gogp_handle* h, const double* theta_simil, const double*
 gogp_status gogp_lml(gogp_handle* h, double* lml) {
     if (!h || !lml) return GOGP_BAD_ARGUMENT;
     if (!h->factored) return fail(h, GOGP_NOT_READY, "LML before Observe/Absorb");
+    if (!h->have_lml) return fail(h, GOGP_NOT_READY, "LML needs Y: the state was restored with gogp_set_state");
     *lml = h->lml;
     return GOGP_OK;
 }
@@ -624,6 +739,7 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
     if (!h || (!grad && len > 0)) return GOGP_BAD_ARGUMENT;
     CK(cudaSetDevice(h->dev));
     if (!h->factored) return fail(h, GOGP_NOT_READY, "Gradient before Observe");
+    if (!h->have_lml) return fail(h, GOGP_NOT_READY, "Gradient needs Y: the state was restored with gogp_set_state");
     const int P = h->nts + h->ntn;
     const int64_t N = h->N, Npad = h->Npad;
     const int D = h->ndim;
@@ -788,7 +904,7 @@ gogp_status gogp_optimize(gogp_handle* h, const gogp_opt_settings* st, double* l
         double lml = 0.0;
         const gogp_status e = gogp_observe(h, x, 0, nullptr, nullptr, 0, &lml);
         if (e != GOGP_OK) {
-            if (e != GOGP_NOT_POSITIVE_DEFINITE) hard = e;
+            if (e != GOGP_NOT_POSITIVE_DEFINITE && e != GOGP_ILL_CONDITIONED) hard = e;
             return false;
         }
         if (prior) {
@@ -834,6 +950,45 @@ gogp_status gogp_get_alpha(gogp_handle* h, double* alpha, int64_t N) {
     CK(cudaSetDevice(h->dev));
     CK(cudaMemcpyAsync(alpha, h->dAlpha, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return GOGP_OK;
+}
+
+gogp_status gogp_set_state(gogp_handle* h, const double* theta_simil, const double* theta_noise, const double* X,
+                           int64_t N, const double* alpha, const double* Lf) {
+    if (!h || N < 0) return GOGP_BAD_ARGUMENT;
+    if (N > 0 && (!X || !alpha || !Lf)) return fail(h, GOGP_BAD_ARGUMENT, "X, alpha and L must be given when N > 0");
+    CK(cudaSetDevice(h->dev));
+    std::vector<double> ts(h->nts > 0 ? h->nts : 1, 0.0), tn(h->ntn > 0 ? h->ntn : 1, 0.0);
+    if (theta_simil)
+        for (int i = 0; i < h->nts; ++i) ts[i] = theta_simil[i];
+    if (theta_noise)
+        for (int i = 0; i < h->ntn; ++i) tn[i] = theta_noise[i];
+    set_theta(h, ts.data(), tn.data());
+    std::vector<double> y0((size_t)(N > 0 ? N : 1), 0.0);  // the stored state has no Y (Produce does not need it)
+    gogp_status st = upload_data(h, X, y0.data(), N);
+    if (st != GOGP_OK) return st;
+    h->with_obs = false;
+    h->have_lml = false;
+    h->lml = 0.0;
+    if (N == 0) {
+        h->factored = true;
+        h->have_lml = true;
+        return GOGP_OK;
+    }
+    const int64_t Npad = h->Npad;
+    cudaStream_t s = h->stream;
+    // L: N x N row-major lower -> dA (ld = Npad), identity in the padding, tile inverses rebuilt
+    CK(cudaMemsetAsync(h->dA, 0, (size_t)Npad * Npad * sizeof(double), s));
+    CK(cudaMemcpy2DAsync(h->dA, (size_t)Npad * sizeof(double), Lf, (size_t)N * sizeof(double), (size_t)N * sizeof(double),
+                         (size_t)N, cudaMemcpyHostToDevice, s));
+    if (Npad > N) launch_fill_diag(h->dA + N * Npad + N, Npad + 1, (int)(Npad - N), 1.0, s);
+    launch_tile_inverse(h->dA, Npad, h->dWinv, (int)(Npad / TILE), s);
+    CK(cudaMemsetAsync(h->dAlpha, 0, (size_t)Npad * sizeof(double), s));
+    CK(cudaMemcpyAsync(h->dAlpha, alpha, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s));
+    h->launches += 2;
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    h->factored = true;
     return GOGP_OK;
 }
 

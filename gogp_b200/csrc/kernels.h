@@ -103,9 +103,14 @@ void launch_fill(double* v, int64_t n, double value, cudaStream_t s);
 void launch_fill_diag(double* v, int64_t stride, int n, double value, cudaStream_t s);
 // pseudo-random fill in (-0.5, 0.5) for microbenchmarks
 void launch_fill_pattern(double* v, int64_t n, cudaStream_t s);
-// out[0] = sum_i log L_ii (i < N), out[1] = sum_i y_i alpha_i
+// out[0] = sum_i log L_ii (i < N), out[1] = sum_i y_i alpha_i, out[2] / out[3] = min / max L_ii
 void launch_logdet_dot(const double* L, int64_t ld, const double* y, const double* alpha, int64_t N, double* out,
                        cudaStream_t s);
+// out = L v (transposed: L^T v) with the lower triangle of L, first N rows / columns (condition estimate)
+void launch_trmv_lower(const double* L, int64_t ld, const double* v, double* out, int64_t N, bool transposed,
+                       cudaStream_t s);
+// winv[t] = (diagonal tile t of L)^-1 for t < tiles (gogp_set_state)
+void launch_tile_inverse(const double* L, int64_t ld, double* winv, int tiles, cudaStream_t s);
 // row reductions of a Mpad x Npad matrix: out[m] = sum_i B[m][i] * (v ? v[i] : B[m][i])
 void launch_row_reduce(const double* B, int64_t ld, int64_t rows, int64_t cols, const double* v, double* out,
                        cudaStream_t s);

@@ -215,26 +215,79 @@ __global__ void __launch_bounds__(1024) logdet_dot_kernel(const double* __restri
                                                           const double* __restrict__ y,
                                                           const double* __restrict__ alpha, int64_t N,
                                                           double* __restrict__ out) {
-    __shared__ double a[1024], b[1024];
-    double s0 = 0.0, s1 = 0.0;
+    __shared__ double a[1024], b[1024], lo[1024], hi[1024];
+    double s0 = 0.0, s1 = 0.0, mn = INFINITY, mx = 0.0;
     for (int64_t i = threadIdx.x; i < N; i += 1024) {
-        s0 += log(L[i * ld + i]);
+        const double d = L[i * ld + i];
+        s0 += log(d);
+        mn = fmin(mn, d);
+        mx = fmax(mx, d);
         if (y) s1 += y[i] * alpha[i];
     }
     a[threadIdx.x] = s0;
     b[threadIdx.x] = s1;
+    lo[threadIdx.x] = mn;
+    hi[threadIdx.x] = mx;
     __syncthreads();
     for (int o = 512; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
             a[threadIdx.x] += a[threadIdx.x + o];
             b[threadIdx.x] += b[threadIdx.x + o];
+            lo[threadIdx.x] = fmin(lo[threadIdx.x], lo[threadIdx.x + o]);
+            hi[threadIdx.x] = fmax(hi[threadIdx.x], hi[threadIdx.x + o]);
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         out[0] = a[0];
         out[1] = b[0];
+        out[2] = lo[0];  // extreme diagonal entries of L: (max / min)^2 is a lower bound of cond_2(K)
+        out[3] = hi[0];
     }
+}
+
+// ---- pieces of the condition estimate (capi.cu cond_estimate; rare path, plain bandwidth kernels) ----
+// w[j] = sum_{i >= j} L[i][j] v[i]  (L^T v): a thread per column, coalesced across the threads of a row
+__global__ void __launch_bounds__(256) trmv_t_kernel(const double* __restrict__ L, int64_t ld,
+                                                     const double* __restrict__ v, double* __restrict__ w, int64_t N) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    double s = 0.0;
+    for (int64_t i = j; i < N; ++i) s = fma(L[i * ld + j], v[i], s);
+    w[j] = s;
+}
+// u[i] = sum_{j <= i} L[i][j] w[j]  (L w): a warp per row
+__global__ void __launch_bounds__(256) trmv_kernel(const double* __restrict__ L, int64_t ld,
+                                                   const double* __restrict__ w, double* __restrict__ u, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= N) return;
+    double s = 0.0;
+    for (int64_t j = lane; j <= i; j += 32) s = fma(L[i * ld + j], w[j], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) u[i] = s;
+}
+// W = T^-1 for the 128 x 128 lower-triangular diagonal tiles of L (gogp_set_state: the tile inverses the
+// blocked solves multiply with are not part of the stored state): one CTA per tile, a thread per column of W,
+// forward substitution through shared memory.
+__global__ void __launch_bounds__(TILE) tile_inverse_kernel(const double* __restrict__ L, int64_t ld,
+                                                            double* __restrict__ winv) {
+    extern __shared__ double sh[];  // T [128][129], then W column-major [128][129]
+    double* T = sh;
+    double* W = sh + TILE * (TILE + 1);
+    const int t = blockIdx.x, c = threadIdx.x;
+    const double* Lt = L + (int64_t)t * TILE * ld + (int64_t)t * TILE;
+    for (int r = 0; r < TILE; ++r) T[r * (TILE + 1) + c] = c <= r ? Lt[(int64_t)r * ld + c] : 0.0;
+    __syncthreads();
+    double* wc = W + c * (TILE + 1);
+    for (int i = 0; i < TILE; ++i) {
+        double s = i == c ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) s = fma(-T[i * (TILE + 1) + k], wc[k], s);
+        wc[i] = i >= c ? s / T[i * (TILE + 1) + i] : 0.0;
+    }
+    __syncthreads();
+    double* out = winv + (int64_t)t * TILE * TILE;
+    for (int r = 0; r < TILE; ++r) out[r * TILE + c] = W[c * (TILE + 1) + r];
 }
 
 __global__ void __launch_bounds__(256) row_reduce_kernel(const double* __restrict__ B, int64_t ld, int64_t rows,
@@ -391,6 +444,28 @@ void launch_trsv_lower(const double* L, int64_t ld, const double* winv, double* 
 void launch_logdet_dot(const double* L, int64_t ld, const double* y, const double* alpha, int64_t N, double* out,
                        cudaStream_t s) {
     logdet_dot_kernel<<<1, 1024, 0, s>>>(L, ld, y, alpha, N, out);
+}
+
+void launch_trmv_lower(const double* L, int64_t ld, const double* v, double* out, int64_t N, bool transposed,
+                       cudaStream_t s) {
+    if (N <= 0) return;
+    if (transposed)
+        trmv_t_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>(L, ld, v, out, N);
+    else
+        trmv_kernel<<<(int)((N + 7) / 8), 256, 0, s>>>(L, ld, v, out, N);
+}
+
+void launch_tile_inverse(const double* L, int64_t ld, double* winv, int tiles, cudaStream_t s) {
+    if (tiles <= 0) return;
+    const size_t smem = (size_t)2 * TILE * (TILE + 1) * sizeof(double);
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63].load(std::memory_order_acquire)) {
+        cudaFuncSetAttribute(tile_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63].store(true, std::memory_order_release);
+    }
+    tile_inverse_kernel<<<tiles, TILE, smem, s>>>(L, ld, winv);
 }
 
 void launch_row_reduce(const double* B, int64_t ld, int64_t rows, int64_t cols, const double* v, double* out,

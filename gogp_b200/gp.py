@@ -256,6 +256,34 @@ class GP:
         return {"iters": result.iters, "evals": result.evals, "grads": result.grads, "lml0": result.lml0,
                 "lml": result.lml, "converged": bool(result.converged)}
 
+    # -- gp/gp.go:35-36, 255-257: "Produce works on stored results" ---------------------------
+    def State(self):
+        """What the reference lets a user keep: the exported L and Alpha (plus the parameters and inputs they
+        belong to).  L is the N x N row-major lower Cholesky factor."""
+        n = self._n
+        return {"ThetaSimil": list(self.ThetaSimil), "ThetaNoise": list(self.ThetaNoise),
+                "X": np.array(_flat(self.X, self.NDim)).reshape(n, self.NDim), "Alpha": self.Alpha(), "L": self.L()}
+
+    def Restore(self, state):
+        """Restore a stored state before Produce; returns None or a GoGPError."""
+        h = self._handle()
+        X = _flat(state["X"], self.NDim)
+        alpha = _flat(state["Alpha"], 0)
+        n = len(alpha)
+        Lf = np.ascontiguousarray(np.asarray(state["L"], dtype=np.float64))
+        if X.size != n * self.NDim or Lf.shape != (n, n):
+            return GoGPError(_lib.BAD_ARGUMENT, "state shapes do not agree")
+        self.ThetaSimil, self.ThetaNoise = list(state["ThetaSimil"]), list(state["ThetaNoise"])
+        ts = np.array(self.ThetaSimil if self._nts() else [0.0], dtype=np.float64)
+        tn = np.array(self.ThetaNoise if self._ntn() else [0.0], dtype=np.float64)
+        st = _lib.lib().gogp_set_state(h, _lib.dptr(ts), _lib.dptr(tn), _lib.dptr(X), n, _lib.dptr(alpha),
+                                       _lib.dptr(Lf.reshape(-1)))
+        if st != _lib.OK:
+            return GoGPError(st, self._err(st))
+        self.X = X.reshape(n, self.NDim)
+        self._with_obs, self._n = False, n
+        return None
+
     # -- extras over the C-ABI ---------------------------------------------------------
     def PhaseTimes(self):
         ms = np.zeros(len(_lib.PHASES))
@@ -271,6 +299,16 @@ class GP:
         if st != _lib.OK:
             raise GoGPPanic(st, self._err(st))
         return a
+
+    def L(self):
+        """The N x N row-major lower Cholesky factor (the reference's exported gp.L, gp/gp.go:35)."""
+        n = self._n
+        out = np.zeros((n, n))
+        if n:
+            st = _lib.lib().gogp_get_factor(self._handle(), _lib.dptr(out.reshape(-1)), n)
+            if st != _lib.OK:
+                raise GoGPPanic(st, self._err(st))
+        return out
 
 
 class Model:

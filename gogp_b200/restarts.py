@@ -59,11 +59,13 @@ def gather_results(lmls, thetas, rank=0, world=1, dist=None):
     if world > 1:
         import torch
         mine = torch.from_numpy(np.concatenate([lmls[:, None], thetas], axis=1))
+        if dist.get_backend() == "nccl":  # NCCL moves device memory only: stage the (tiny) payload on this rank's GPU
+            mine = mine.cuda()
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
         for w, part in enumerate(parts):
             idx = shard(R, w, world)
-            a = part.numpy()
+            a = part.cpu().numpy()
             lmls[idx] = a[idx, 0]
             thetas[idx] = a[idx, 1:]
     return lmls, thetas, int(np.argmax(lmls))
@@ -72,6 +74,6 @@ def gather_results(lmls, thetas, rank=0, world=1, dist=None):
 def multi_start(evaluate, starts, rank=0, world=1, iters=0, dist=None, optimise=None):
     """Run this rank's share of `starts` and gather all results.  Returns (lmls[R],
     thetas[R, P], best index); every rank gets the same answer.  `dist` is torch.distributed
-    (any backend) or None."""
+    (gloo: host tensors; nccl: the payload is staged on the current CUDA device) or None."""
     lmls, thetas = run_share(evaluate, starts, rank, world, iters, optimise)
     return gather_results(lmls, thetas, rank, world, dist)

@@ -32,7 +32,8 @@ typedef enum {
     GOGP_OK = 0,
     GOGP_BAD_ARGUMENT = 1,          /* Observe's panic("len(x)"), gp/gp.go:398-400 */
     GOGP_NOT_POSITIVE_DEFINITE = 2, /* Factorize(K) == false, gp/gp.go:228-230 */
-    GOGP_ILL_CONDITIONED = 3,       /* reserved: gonum's Condition error, gp/gp.go:233-236 */
+    GOGP_ILL_CONDITIONED = 3,       /* gonum's Condition error (cond > 1e16) from SolveVecTo, gp/gp.go:233-236: the
+                                       factor, alpha and LML are complete, as there; estimated from below */
     GOGP_CUDA_ERROR = 4,
     GOGP_NCCL_ERROR = 5,
     GOGP_OUT_OF_MEMORY = 6,
@@ -145,6 +146,13 @@ gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu,
 gogp_status gogp_get_alpha(gogp_handle* h, double* alpha, int64_t N);
 gogp_status gogp_get_factor(gogp_handle* h, double* L, int64_t N);
 
+/* "Produce on stored results": the reference exports L and Alpha so that a user can keep them and restore them
+ * before Produce (gp/gp.go:35-36, 255-257).  Restores what gogp_get_alpha / gogp_get_factor returned together
+ * with the natural-scale parameters and the inputs; gogp_produce then works as after Absorb.  No Y is stored,
+ * so gogp_lml and gogp_gradient report GOGP_NOT_READY until the next Observe / Absorb. */
+gogp_status gogp_set_state(gogp_handle* h, const double* theta_simil, const double* theta_noise, const double* X,
+                           int64_t N, const double* alpha, const double* L);
+
 const char* gogp_last_error(const gogp_handle* h);
 const char* gogp_status_string(gogp_status s);
 gogp_status gogp_phase_times(const gogp_handle* h, double* ms /* GOGP_NPHASE */);
@@ -206,7 +214,7 @@ gogp_status gogp_dev_gemm_bc(gogp_handle* h, double* C, int64_t ldc, const doubl
 /* Pre-allocate the scratch gogp_dev_trsm needs for right-hand sides of up to `rows` rows, so that no allocation
  * happens between collectives. */
 gogp_status gogp_dev_reserve(gogp_handle* h, int64_t rows);
-/* out[0] = sum_{i < nvalid} log L_ii of a factored block. */
+/* out[0] = sum_{i < nvalid} log L_ii of a factored block (out: 4 doubles; [2], [3] = min, max L_ii). */
 gogp_status gogp_dev_sumlogdiag(gogp_handle* h, const double* L, int64_t ld, int64_t nvalid, double* out,
                                 void* stream);
 /* Block forward-substitution pieces for z = L^-1 y:  acc[r] -= sum_c B[r][c] v[c]  (rows x cols block),

@@ -139,9 +139,40 @@ public:
         Error e = handle();
         if (!e.ok()) return e;
         std::vector<double> xf = flatten(x);
+        // the C-ABI takes one N for both buffers: a ragged x or len(x) != len(y) must not reach it
+        if (xf.size() != y.size() * (size_t)NDim) return bad("len(x) != len(y) (or a row of x is not NDim long)");
         withObs_ = false;
         n_ = (int64_t)y.size();
         return wrap(gogp_absorb(h_, ThetaSimil.data(), ThetaNoise.data(), xf.data(), y.data(), n_));
+    }
+
+    // gp/gp.go:35-36, 255-257: the exported results a user may store, and "Produce works on stored results"
+    std::vector<double> Alpha() {
+        std::vector<double> a((size_t)n_, 0.0);
+        if (h_ && n_ > 0 && gogp_get_alpha(h_, a.data(), n_) != GOGP_OK) throw Panic(GOGP_NOT_READY, gogp_last_error(h_));
+        return a;
+    }
+    std::vector<double> L() {  // n x n row-major, lower
+        std::vector<double> l((size_t)n_ * (size_t)n_, 0.0);
+        if (h_ && n_ > 0 && gogp_get_factor(h_, l.data(), n_) != GOGP_OK) throw Panic(GOGP_NOT_READY, gogp_last_error(h_));
+        return l;
+    }
+    Error Restore(const std::vector<double>& thetaSimil, const std::vector<double>& thetaNoise,
+                  const std::vector<std::vector<double>>& x, const std::vector<double>& alpha,
+                  const std::vector<double>& l) {
+        Error e = handle();
+        if (!e.ok()) return e;
+        std::vector<double> xf = flatten(x);
+        const size_t n = alpha.size();
+        if (xf.size() != n * (size_t)NDim || l.size() != n * n || thetaSimil.size() != (size_t)Simil.NTheta() ||
+            thetaNoise.size() != (size_t)noiseNTheta())
+            return bad("state shapes do not agree");
+        ThetaSimil = thetaSimil;
+        ThetaNoise = thetaNoise;
+        X = x;
+        withObs_ = false;
+        n_ = (int64_t)n;
+        return wrap(gogp_set_state(h_, ThetaSimil.data(), ThetaNoise.data(), xf.data(), n_, alpha.data(), l.data()));
     }
 
     // gp/gp.go:244-253
@@ -157,6 +188,7 @@ public:
         Error e = handle();
         if (!e.ok()) return e;
         std::vector<double> zf = flatten(x);
+        if (zf.size() != x.size() * (size_t)NDim) return bad("a row of x is not NDim long");
         mu.assign(x.size(), 0.0);
         sigma.assign(x.size(), 0.0);
         return wrap(gogp_produce(h_, zf.data(), (int64_t)x.size(), mu.data(), sigma.data()));
@@ -196,6 +228,7 @@ public:
             Y.assign(yp, yp + n);
         } else {
             xf = flatten(X);
+            if (xf.size() != Y.size() * (size_t)NDim) throw Panic(GOGP_BAD_ARGUMENT, "len(gp.X) != len(gp.Y)");
             n_ = (int64_t)Y.size();
             xp = xf.data();
             yp = Y.data();
@@ -227,6 +260,7 @@ public:
         const size_t P = (size_t)Simil.NTheta() + (size_t)noiseNTheta();
         if (x.size() != P) throw Panic(GOGP_BAD_ARGUMENT, "len(x)");
         std::vector<double> xf = flatten(X);
+        if (xf.size() != Y.size() * (size_t)NDim) throw Panic(GOGP_BAD_ARGUMENT, "len(gp.X) != len(gp.Y)");
         gogp_status st = gogp_set_data(h_, xf.data(), Y.data(), (int64_t)Y.size());
         if (st != GOGP_OK) throw Panic(st, gogp_last_error(h_));
         gogp_opt_settings s{};
@@ -261,6 +295,12 @@ private:
         out.reserve(x.size() * (size_t)NDim);
         for (const auto& r : x) out.insert(out.end(), r.begin(), r.end());
         return out;
+    }
+    static Error bad(const char* msg) {
+        Error e;
+        e.status = GOGP_BAD_ARGUMENT;
+        e.message = msg;
+        return e;
     }
     Error wrap(gogp_status st) const {
         Error e;

@@ -68,6 +68,23 @@ int main(int argc, char** argv) {
         bad.ThetaSimil = {1.0};
         e = bad.Absorb({{0}, {0}}, {1, 2});  // singular K: an error, not a panic, from Absorb
         CHECK(!e.ok() && e.status == GOGP_NOT_POSITIVE_DEFINITE);
+        // len(x) != len(y) and a ragged x are errors of the wrapper: the C-ABI takes one N for both buffers
+        e = bad.Absorb({{0}, {1}, {2}}, {1, 2});
+        CHECK(!e.ok() && e.status == GOGP_BAD_ARGUMENT);
+        e = bad.Absorb({{0}, {1, 5}}, {1, 2});
+        CHECK(!e.ok() && e.status == GOGP_BAD_ARGUMENT);
+        // "Produce works on stored results" (gp/gp.go:255-257): restore L and Alpha into a fresh GP
+        std::vector<double> alpha = g.Alpha(), l = g.L();
+        CHECK(alpha.size() == 2 && l.size() == 4 && l[1] == 0.0);
+        GP r(1, Normal, ConstantNoise(0.1));
+        e = r.Restore({1.0}, {}, {{0}, {1}}, alpha, l);
+        CHECK(e.ok());
+        std::vector<double> mu2, sigma2;
+        e = r.Produce({{-2.}, {3.}}, mu2, sigma2);
+        CHECK(e.ok());
+        CHECK(std::fabs(mu2[0] - mu[0]) < 1e-12 && std::fabs(sigma2[1] - sigma[1]) < 1e-12);
+        e = r.Restore({1.0}, {}, {{0}, {1}}, alpha, {1.0});
+        CHECK(!e.ok() && e.status == GOGP_BAD_ARGUMENT);
     }
     std::printf(fails ? "FAILED %d\n" : "all ok\n", fails);
     return fails ? 1 : 0;

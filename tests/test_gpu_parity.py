@@ -420,3 +420,62 @@ def test_produce_chunks_many_test_points():
     mref, sref = og.produce(Z, clamp=True)
     assert np.max(np.abs(mu - mref)) <= PRED_TOL * max(1.0, np.abs(mref).max())
     assert np.max(np.abs(sigma ** 2 - sref ** 2)) <= PRED_TOL * max(1.0, np.abs(sref).max() ** 2)
+
+
+def test_produce_on_stored_results():
+    """gp/gp.go:255-257: "Produce works on stored results" -- L and Alpha are exported so that a user can keep them
+    and restore them before Produce.  A second GP restored from State() predicts what the first one does."""
+    from gogp_b200 import GoGPPanic, _lib
+    name, N = "hyperpriors", 300
+    X, y, logt = cases.synth(name, N, seed=21)
+    dg = cases.make_device_gp(name)
+    dg.X, dg.Y = X, y
+    dg.Observe(logt.copy())
+    Z = np.linspace(X.min() - 1.0, X.max() + 1.0, 200).reshape(-1, 1)
+    mu, sigma, err = dg.Produce(Z)
+    assert err is None
+    state = dg.State()
+    assert state["L"].shape == (N, N) and np.allclose(np.triu(state["L"], 1), 0.0)
+    dg.close()
+    g2 = cases.make_device_gp(name)
+    assert g2.Restore(state) is None
+    mu2, sigma2, err = g2.Produce(Z)
+    assert err is None
+    assert np.max(np.abs(mu2 - mu)) <= 1e-10 * max(1.0, np.abs(mu).max())
+    assert np.max(np.abs(sigma2 ** 2 - sigma ** 2)) <= 1e-10
+    with pytest.raises(GoGPPanic) as e:      # no Y in the stored state
+        g2.LML()
+    assert e.value.status == _lib.NOT_READY
+    with pytest.raises(GoGPPanic):
+        g2.Gradient()
+    bad = dict(state)
+    bad["Alpha"] = state["Alpha"][:-1]
+    assert g2.Restore(bad) is not None
+    # and the restored handle goes on working as a GP
+    g2.X, g2.Y = X, y
+    og = cases.make_oracle_gp(name)
+    og.X, og.Y = X, y
+    assert abs(g2.Observe(logt.copy()) - og.observe(logt.copy())) <= LML_TOL * N
+    g2.close()
+
+
+def test_ill_conditioned_is_an_error_with_a_complete_state():
+    """gonum's SolveVecTo returns a Condition error when cond(K) > 1e16 and the reference passes it on
+    (gp/gp.go:233-236: Absorb returns it, Observe panics); the factor, alpha and LML exist all the same.
+    K = 1 1^T + s I (N identical inputs): cond_2 = (N + s) / s; s = 1e-13 -> 4e16, s = 1e-9 -> 4e12."""
+    from gogp_b200 import GP, GoGPPanic, _lib, kernel as k
+    N = 4096
+    X = np.zeros((N, 1))
+    y = np.sin(np.arange(N) * 0.01)
+    g = GP(NDim=1, Simil=k.Normal, Noise=k.ConstantNoise(np.sqrt(1e-13)), ThetaSimil=[1.0])
+    err = g.Absorb(X, y)
+    assert err is not None and err.status == _lib.ILL_CONDITIONED, err
+    assert "condition number" in str(err)
+    assert np.isfinite(g.LML())
+    with pytest.raises(GoGPPanic) as e:
+        g.Observe(np.array([0.0]))
+    assert e.value.status == _lib.ILL_CONDITIONED
+    g.close()
+    g = GP(NDim=1, Simil=k.Normal, Noise=k.ConstantNoise(np.sqrt(1e-9)), ThetaSimil=[1.0])
+    assert g.Absorb(X, y) is None          # suspicious diagonal (stage 1), cleared by the estimate (stage 2)
+    g.close()

@@ -150,3 +150,21 @@ def test_blocked_potrf_flags_non_pd(cpu_blocked):
     K[200, 200] = -1.0
     winv = np.zeros((2, 128, 128))
     assert cpu_blocked.cpu_blocked_potrf(_p(K), C.c_int64(n), _p(winv)) == 201
+
+
+def test_grid_has_no_cpu_fallback_either(built_lib):
+    """gogp_create_grid on a machine without a GPU fails loudly (and an impossible grid shape is rejected first)."""
+    import torch
+    import gogp_b200 as g
+    from gogp_b200 import kernel as k
+    with pytest.raises(g.GoGPPanic) as e:
+        g.GridGP(NDim=1, Simil=k.Normal, Noise=None, Devices=[0], Grid=(2, 1))
+    assert e.value.status == g._lib.BAD_ARGUMENT
+    with pytest.raises(g.GoGPPanic) as e:
+        g.GridGP(NDim=1, Simil=k.Normal, Noise=None, Devices=[0], Block=100)
+    assert e.value.status == g._lib.BAD_ARGUMENT
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(g.GoGPPanic) as e:
+        g.GridGP(NDim=1, Simil=k.Normal, Noise=k.ConstantNoise(0.1), Devices=[0])
+    assert e.value.status == g._lib.CUDA_ERROR
