@@ -27,7 +27,7 @@ SYMBOLS = (
     "gogp_produce", "gogp_optimize", "gogp_get_alpha", "gogp_get_factor", "gogp_set_state", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
     "gogp_debug_gemm", "gogp_debug_leaf", "gogp_debug_leaf_run", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
-    "gogp_dev_gemm", "gogp_dev_gemm_bc", "gogp_dev_reserve", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_dev_trtri_t", "gogp_dev_trace_block", "gogp_noise_eval", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
+    "gogp_dev_gemm", "gogp_dev_gemm_bc", "gogp_dev_reserve", "gogp_dev_sumlogdiag", "gogp_dev_gemv_sub", "gogp_dev_trsv", "gogp_dev_trtri_t", "gogp_dev_trace_block", "gogp_dev_trace_local", "gogp_noise_eval", "gogp_timer_start", "gogp_timer_stop", "gogp_profile_enable", "gogp_profile_read",
     "gogp_create_grid", "gogp_grid_unique_id", "gogp_grid_create_rank", "gogp_grid_destroy", "gogp_grid_set_data",
     "gogp_grid_observe", "gogp_grid_gradient", "gogp_grid_absorb", "gogp_grid_lml", "gogp_grid_get_alpha",
     "gogp_grid_phase_times", "gogp_grid_stats", "gogp_grid_last_error",
@@ -131,6 +131,9 @@ def lib():
     L.gogp_dev_trsv.argtypes = [H, vp, i64, vp, vp, vp, i64, vp]
     L.gogp_dev_trtri_t.argtypes = [H, vp, i64, i64, vp, vp, vp]
     L.gogp_dev_trace_block.argtypes = [H, dp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
+    L.gogp_dev_trace_local.argtypes = [H, dp, vp, vp, i64, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                       vp]
+    L.gogp_dev_trace_local.restype = C.c_int
     L.gogp_noise_eval.argtypes = [H, dp, dp, dp]
     for f in (L.gogp_dev_trtri_t, L.gogp_dev_trace_block, L.gogp_noise_eval):
         f.restype = C.c_int

@@ -573,6 +573,9 @@ gogp_status gogp_create(int ndim, const gogp_op* simil, int n_simil_ops, int nth
         def.constant = kNoNoise * kNoNoise;
         h->noise.lower(&def, 1, 0, ndim, false, &err);
     }
+    if (grad_trace_smem_bytes(ndim, ntheta_simil) > 227 * 1024)
+        return fail(h, GOGP_UNSUPPORTED, "ndim and ntheta_simil together exceed the shared memory of the gradient "
+                                         "trace kernel (2 KB per dimension + 2 KB per parameter + 34 KB <= 227 KB)");
     h->nts = ntheta_simil;
     h->ntn = h->noise.ntheta;
     h->theta_s.assign(h->nts > 0 ? h->nts : 1, 0.0);  // defaults(): zero parameters, gp/gp.go:50-56
@@ -1338,6 +1341,26 @@ gogp_status gogp_dev_trace_block(gogp_handle* h, const double* theta_simil, cons
     h->simil.bind(ts.data(), &prog);
     launch_grad_trace_block(prog, h->dXt, h->Npad, alpha, kinv, ld, h->N, h->ndim, row0, (int)(rows / TILE), col0,
                             (int)(cols / TILE), scratch, acc, pick_stream(h, stream));
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return GOGP_OK;
+}
+
+gogp_status gogp_dev_trace_local(gogp_handle* h, const double* theta_simil, const double* alpha, const double* kinv,
+                                 int64_t ld, int64_t rows, int64_t cols, int tb, int r0, int pr, int c0, int pc,
+                                 double* acc, double* scratch, void* stream) {
+    if (!h || !alpha || !kinv || !acc || !scratch || rows <= 0 || cols <= 0 || rows % TILE || cols % TILE || tb < 1 ||
+        pr < 1 || pc < 1 || r0 < 0 || c0 < 0)
+        return GOGP_BAD_ARGUMENT;
+    if (!h->dXt) return fail(h, GOGP_BAD_ARGUMENT, "no inputs: call gogp_dev_set_inputs first");
+    CK(cudaSetDevice(h->dev));
+    std::vector<double> ts(h->nts > 0 ? h->nts : 1, 0.0);
+    if (theta_simil)
+        for (int i = 0; i < h->nts; ++i) ts[i] = theta_simil[i];
+    DevProgram prog;
+    h->simil.bind(ts.data(), &prog);
+    launch_grad_trace_bc(prog, h->dXt, h->Npad, alpha, kinv, ld, h->N, h->ndim, (int)(rows / TILE), (int)(cols / TILE), tb,
+                         r0, pr, c0, pc, scratch, acc, pick_stream(h, stream));
     h->launches += 2;
     CK(cudaGetLastError());
     return GOGP_OK;

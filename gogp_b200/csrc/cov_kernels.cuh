@@ -208,13 +208,42 @@ __global__ void cov_self_kernel(const __grid_constant__ DevProgram prog, const d
 // nothing is reduced across threads until the end of the tile.  dK is never
 // materialised (the reference stores one dense N x N matrix per parameter,
 // gp/gp.go:93-97,158-163).  ~70 KB of shared memory -> 3 CTAs per SM.
+// Which tiles a trace launch walks and where they sit in the global matrix:
+//   mode 0  the whole matrix: CTA b = lower tile (ti, tj), diagonal tiles in kdiag;
+//   mode 1  a rows x cols block whose origin is element (grow0, gcol0): CTA b = tile (b / ctiles, b % ctiles);
+//   mode 2  one rank's local matrix of a pr x pc block-cyclic distribution with tb x tb tiles per block
+//           (grid.hpp): tile (ti, tj) belongs to global block (r0 + pr (ti / tb), c0 + pc (tj / tb)).
+// kinv always points at the launch's own storage (tile (ti, tj) at kinv + ti 128 ld + tj 128); only elements with
+// global row >= global column (< N) count.
+struct TraceMap {
+    int mode, ctiles;
+    int64_t grow0, gcol0;
+    int tb, r0, pr, c0, pc;
+};
+__device__ __forceinline__ void trace_tile(const TraceMap& m, int b, int& ti, int& tj, int64_t& row0, int64_t& col0) {
+    if (m.mode == 0) {
+        lower_tile(b, ti, tj);
+        row0 = (int64_t)ti * TILE;
+        col0 = (int64_t)tj * TILE;
+    } else {
+        ti = b / m.ctiles;
+        tj = b % m.ctiles;
+        if (m.mode == 1) {
+            row0 = m.grow0 + (int64_t)ti * TILE;
+            col0 = m.gcol0 + (int64_t)tj * TILE;
+        } else {
+            row0 = ((int64_t)(m.r0 + m.pr * (ti / m.tb)) * m.tb + ti % m.tb) * TILE;
+            col0 = ((int64_t)(m.c0 + m.pc * (tj / m.tb)) * m.tb + tj % m.tb) * TILE;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__ DevProgram prog,
                                                          const double* __restrict__ Xt, int64_t ldx,
                                                          const double* __restrict__ alpha,
                                                          const double* __restrict__ kinv, int64_t ld,
                                                          const double* __restrict__ kdiag, int64_t N, int D,
-                                                         double* __restrict__ partial, int rect_cols,
-                                                         int64_t grow0, int64_t gcol0) {
+                                                         double* __restrict__ partial, const TraceMap map) {
     GOGP_DYN_SMEM_RAW(smem_raw);
     double* xr = reinterpret_cast<double*>(smem_raw);
     double* xc = xr + D * TILE;
@@ -223,18 +252,10 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
     double* ww = pw + GT_E * 256;                     // [GT_E][256] weights w_e * W_e
     double* acc = ww + GT_E * 256;                    // [ntheta + 1][256] per-thread accumulators
 
-    // whole matrix: lower tiles, diagonal tiles in kdiag.  Block of a distributed matrix
-    // (rect_cols > 0): every tile of a rows x cols block whose origin is element (grow0, gcol0)
-    // of the global matrix; kinv points at the block and holds its diagonal tiles too.
     int ti, tj;
-    if (rect_cols > 0) {
-        ti = blockIdx.x / rect_cols;
-        tj = blockIdx.x % rect_cols;
-    } else {
-        lower_tile(blockIdx.x, ti, tj);
-    }
+    int64_t row0, col0;
+    trace_tile(map, blockIdx.x, ti, tj, row0, col0);
     const int64_t lrow0 = (int64_t)ti * TILE, lcol0 = (int64_t)tj * TILE;
-    const int64_t row0 = grow0 + lrow0, col0 = gcol0 + lcol0;
     const int tid = threadIdx.x;
     const int nslot = prog.ntheta;  // slot ntheta = trace of W
     if (col0 > row0 + TILE - 1) {   // a tile above the diagonal (upper part of a diagonal block): nothing counts
@@ -316,6 +337,175 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const __grid_constant__
     acc[nslot * 256 + tid] = trw;
     __syncthreads();
     // fixed-order tree over the 256 threads of each slot (bit-repeatable)
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int q = 0; q <= nslot; ++q) acc[q * 256 + tid] += acc[q * 256 + tid + o];
+        __syncthreads();
+    }
+    if (tid <= nslot) partial[(int64_t)blockIdx.x * (nslot + 1) + tid] = acc[tid * 256];
+}
+
+// ---- specialised fused trace ---------------------------------------------------------------------
+// ncu showed the interpreted trace above bound by instruction issue (~600 thread instructions per element for the
+// C3 kernel, FP64 pipe 41 %): the descriptor walk, the term value computed in one phase and every transcendental
+// computed AGAIN for the log-derivatives in the next, shared-memory staging of both.  Here, for a product term
+// whose leading NN factors are Normal leaves:
+//   - the Normal factors are unrolled at compile time; d_j^2 is both the exponent's summand and the factor's
+//     log-derivative, so the gradient of a Normal factor costs one FMA on top of the value;
+//   - a bare parameter multiplies the term's coefficient once per CTA and its gradient slot is the plain sum of
+//     the weighted term values;
+//   - the (at most kTraceMaxRest) remaining leaves are evaluated once, value and log-derivatives together
+//     (factor_value_dlog: one sincos + one exp per Periodic, one exp + one reciprocal per Matern);
+//   - everything stays in registers: a thread walks its column pair down the tile one row at a time (2 elements,
+//     independent dependency chains) and flushes its accumulators to its shared-memory cells once per term;
+//   - tiles strictly below the diagonal and inside the data skip the diagonal / padding masks, and the next
+//     row of K^-1 is requested before the current one is used.
+// NN = 0 handles any number of terms (e.g. hyperpriors' Matern52 + Periodic sum).
+// MAXR = how many such leaves the instantiation carries registers for (0, 1 or kTraceMaxRest): the occupancy of this
+// latency-bound kernel is set by its register count (NN = 8: 232 registers and 8 warps per SM measured 11.0 ms at
+// N = 32768 for the C3 kernel, the same code squeezed into 128 registers and 16 warps 8.0 ms).
+constexpr int kTraceMaxRest = 4;
+
+template <int NN, int MAXR, int MINB>
+__global__ void __launch_bounds__(256, MINB) grad_trace_fast_kernel(const __grid_constant__ DevProgram prog,
+                                                                    const double* __restrict__ Xt, int64_t ldx,
+                                                                    const double* __restrict__ alpha,
+                                                                    const double* __restrict__ kinv, int64_t ld,
+                                                                    const double* __restrict__ kdiag, int64_t N, int D,
+                                                                    double* __restrict__ partial, const TraceMap map) {
+    GOGP_DYN_SMEM_RAW(smem_raw);
+    double* xr = reinterpret_cast<double*>(smem_raw);
+    double* xc = xr + D * TILE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(xc + D * TILE);
+    double* acc = reinterpret_cast<double*>(bar + 2);  // [ntheta + 1][256] per-thread cells
+
+    int ti, tj;
+    int64_t row0, col0;
+    trace_tile(map, blockIdx.x, ti, tj, row0, col0);
+    const int tid = threadIdx.x;
+    const int nslot = prog.ntheta;
+    if (col0 > row0 + TILE - 1) {
+        if (tid <= nslot) partial[(int64_t)blockIdx.x * (nslot + 1) + tid] = 0.0;
+        return;
+    }
+    for (int q = 0; q <= nslot; ++q) acc[q * 256 + tid] = 0.0;
+    stage_tiles(xr, xc, bar, Xt, ldx, row0, Xt, ldx, col0, D);
+
+    const bool side_diag = map.mode == 0 && kdiag != nullptr && ti == tj;
+    const double* ktile = side_diag ? kdiag + (int64_t)ti * TILE * TILE : kinv + (int64_t)ti * TILE * ld + (int64_t)tj * TILE;
+    const int64_t kld = side_diag ? TILE : ld;
+    const int c0 = 2 * (tid & 63);
+    const int ir = tid >> 6;
+    const int64_t gj = col0 + c0;
+    const double aj0 = alpha[gj], aj1 = alpha[gj + 1];
+    const bool interior = row0 >= col0 + TILE && row0 + TILE <= N;
+    double trw = 0.0;
+
+    for (int t = 0; t < prog.nterms; ++t) {
+        const int fb = prog.fbeg[t], fe = prog.fbeg[t + 1];
+        // bare parameters fold into the coefficient; ridx[k] = the k-th other factor behind the Normal ones
+        double cterm = prog.coef[t];
+        for (int fi = fb + NN; fi < fe; ++fi)
+            if (prog.f[fi].kind == F_PARAM) cterm *= prog.f[fi].a0;
+        constexpr int MR = MAXR > 0 ? MAXR : 1;
+        int ridx[MR];
+        {
+            int fi = fb + NN;
+#pragma unroll
+            for (int k = 0; k < MAXR; ++k) {
+                while (fi < fe && prog.f[fi].kind == F_PARAM) ++fi;
+                ridx[k] = fi < fe ? fi++ : -1;
+            }
+        }
+        constexpr int NR = NN > 0 ? NN : 1;
+        int rofs[NR];
+        double accN[NR];
+#pragma unroll
+        for (int j = 0; j < NN; ++j) {
+            rofs[j] = prog.f[fb + j].dim * TILE;
+            accN[j] = 0.0;
+        }
+        double accR0[MR], accR1[MR];
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) accR0[k] = accR1[k] = 0.0;
+        double sP = 0.0;
+
+        double2 kv = *reinterpret_cast<const double2*>(ktile + (int64_t)ir * kld + c0);
+        for (int rr = 0; rr < TILE / 4; ++rr) {
+            const int r = rr * 4 + ir;
+            const int64_t gi = row0 + r;
+            const double2 kc = kv;
+            if (rr + 1 < TILE / 4) kv = *reinterpret_cast<const double2*>(ktile + (int64_t)(r + 4) * kld + c0);
+            const double ai = alpha[gi];
+            double w0 = ai * aj0 - kc.x, w1 = ai * aj1 - kc.y;
+            if (!interior) {
+                const bool in0 = gi < N && gj < N && gi >= gj, in1 = gi < N && gj + 1 < N && gi >= gj + 1;
+                if (!in0) w0 = 0.0;
+                if (!in1) w1 = 0.0;
+                if (gi == gj) {
+                    if (t == 0) trw += w0;
+                    w0 *= 0.5;
+                }
+                if (gi == gj + 1) {
+                    if (t == 0) trw += w1;
+                    w1 *= 0.5;
+                }
+            }
+            double p0 = cterm, p1 = cterm;
+            double e0[NR], e1[NR];
+            if (NN > 0) {
+                double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NN; ++j) {
+                    const double xb = xr[rofs[j] + r], inv = prog.f[fb + j].i0;
+                    const double d0 = (xc[rofs[j] + c0] - xb) * inv, d1 = (xc[rofs[j] + c0 + 1] - xb) * inv;
+                    e0[j] = d0 * d0;
+                    e1[j] = d1 * d1;
+                    q0 += e0[j];
+                    q1 += e1[j];
+                }
+                p0 *= exp(-q0 / 2);
+                p1 *= exp(-q1 / 2);
+            }
+            double g00[MR], g01[MR], g10[MR], g11[MR];
+#pragma unroll
+            for (int k = 0; k < MAXR; ++k) {
+                g00[k] = g01[k] = g10[k] = g11[k] = 0.0;
+                if (ridx[k] >= 0) {
+                    const DevFactor& f = prog.f[ridx[k]];
+                    const double xb = xr[f.dim * TILE + r];
+                    double v0, v1;
+                    factor_value_dlog(prog, f, xc[f.dim * TILE + c0], xb, v0, g00[k], g01[k]);
+                    factor_value_dlog(prog, f, xc[f.dim * TILE + c0 + 1], xb, v1, g10[k], g11[k]);
+                    p0 *= v0;
+                    p1 *= v1;
+                }
+            }
+            const double wp0 = w0 * p0, wp1 = w1 * p1;
+            sP += wp0 + wp1;
+#pragma unroll
+            for (int j = 0; j < NN; ++j) accN[j] = fma(wp0, e0[j], fma(wp1, e1[j], accN[j]));
+#pragma unroll
+            for (int k = 0; k < MAXR; ++k) {
+                accR0[k] = fma(wp0, g00[k], fma(wp1, g10[k], accR0[k]));
+                accR1[k] = fma(wp0, g01[k], fma(wp1, g11[k], accR1[k]));
+            }
+        }
+        // flush this term's sums into the thread's own cells
+#pragma unroll
+        for (int j = 0; j < NN; ++j) acc[prog.f[fb + j].p0 * 256 + tid] += accN[j];
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k)
+            if (ridx[k] >= 0) {
+                const DevFactor& f = prog.f[ridx[k]];
+                if (f.p0 >= 0) acc[f.p0 * 256 + tid] += accR0[k];
+                if (f.p1 >= 0) acc[f.p1 * 256 + tid] += accR1[k];
+            }
+        for (int fi = fb + NN; fi < fe; ++fi)
+            if (prog.f[fi].kind == F_PARAM) acc[prog.f[fi].p0 * 256 + tid] += sP;
+    }
+    acc[nslot * 256 + tid] = trw;
+    __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
         if (tid < o)
             for (int q = 0; q <= nslot; ++q) acc[q * 256 + tid] += acc[q * 256 + tid + o];

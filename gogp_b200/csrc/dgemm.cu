@@ -27,15 +27,15 @@ namespace {
 
 #include "dgemm_kernels.cuh"
 
-template <int WM, int WN, int STAGES, int MINB>
+template <int WM, int WN, int STAGES, int MINB, int FM = 8>
 void launch_cfg(const GemmArgs& g0, int64_t m, int64_t n, cudaStream_t s) {
-    constexpr int BM = 64 * WM, BN = 32 * WN;
+    constexpr int BM = 8 * FM * WM, BN = 32 * WN;
     constexpr size_t SMEM = (size_t)STAGES * (BM + BN) * PITCH * sizeof(double);
     static std::atomic<bool> configured[64];  // the attribute is per device; handles on other threads may race here
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63].load(std::memory_order_acquire)) {
-        cudaFuncSetAttribute(dgemm_nt_kernel<WM, WN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(dgemm_nt_kernel<WM, WN, STAGES, MINB, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SMEM);
         configured[dev & 63].store(true, std::memory_order_release);
     }
@@ -45,7 +45,7 @@ void launch_cfg(const GemmArgs& g0, int64_t m, int64_t n, cudaStream_t s) {
     const int ratio = BM / BN;
     const int ntiles = (g.mode & GEMM_LOWER) ? ratio * g.tm * (g.tm + 1) / 2 : g.tm * g.tn;
     if (ntiles <= 0) return;
-    dgemm_nt_kernel<WM, WN, STAGES, MINB><<<ntiles, WM * WN * 32, SMEM, s>>>(g);
+    dgemm_nt_kernel<WM, WN, STAGES, MINB, FM><<<ntiles, WM * WN * 32, SMEM, s>>>(g);
 }
 
 // ---- FP64 peak microbenchmarks (registers only) --------------------------------------
@@ -101,7 +101,20 @@ void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const
         }
     });
     if (k <= 0) return;
-    if (g_gemm_cfg == 2 && k >= tma_min_k &&
+    // Latency shapes: a launch of a few 128 x 128 tiles is bound by one SM's DMMA rate per tile, not by the GPU's;
+    // quarter tiles with 32 x 32 warp tiles spread it over 4x the SMs (GOGP_SMALL_TILES: at most this many
+    // 128-tiles, default 36 = a quarter of the SMs; 0 switches the shapes off).
+    static int64_t small_tiles = 36;
+    static std::once_flag small_knob;
+    std::call_once(small_knob, [] {
+        const char* e = getenv("GOGP_SMALL_TILES");
+        if (e) small_tiles = atoll(e);
+    });
+    const int64_t tm128 = m / TILE, tn128 = n / TILE;
+    const int64_t tiles128 = (mode & GEMM_LOWER) ? tm128 * (tm128 + 1) / 2 : tm128 * tn128;
+    const bool small = tiles128 <= small_tiles && !(mode & GEMM_DIAG_OUT) && !(mask && mask->tb > 0) &&
+                       (!(mode & GEMM_INPLACE) || n == TILE);
+    if (!small && g_gemm_cfg == 2 && k >= tma_min_k &&
         launch_dgemm_tma(C, ldc, A, lda, B, ldb, m, n, k, alpha, beta, mode, cdiag, s, mask))
         return;
     GemmArgs g;
@@ -123,6 +136,13 @@ void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const
         g.mpr = mask->pr;
         g.mc0 = mask->c0;
         g.mpc = mask->pc;
+    }
+    if (small) {
+        if (mode & GEMM_INPLACE)
+            launch_cfg<1, 4, 3, 2, 4>(g, m, n, s);  // 32 x 128: the CTA owns entire rows of the 128-wide block
+        else
+            launch_cfg<2, 2, 3, 3, 4>(g, m, n, s);  // 64 x 64
+        return;
     }
     // C aliasing A needs a CTA that owns entire rows of the (128-wide) block
     if (g_gemm_cfg == 0 || (mode & GEMM_INPLACE))  // (cfg 2 falls back to the 2-CTA shape below)

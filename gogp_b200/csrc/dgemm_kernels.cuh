@@ -58,9 +58,15 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 //              (in-place solve with a diagonal block: one CTA must own whole rows);
 //   <2,2,3,2>  128 x 64, 128 threads, 3 stages (90 KB), 2 CTAs/SM: the two resident CTAs
 //              synchronise independently, so one computes while the other sits at its barrier.
-template <int WM, int WN, int STAGES, int MINB>
+//   <2,2,3,4,4> 64 x 64 and <1,4,3,3,4> 32 x 128 (in place) with 32 x 32 warp tiles (FM = 4 fragment rows): the
+//              LATENCY shapes.  A launch with a handful of 128 x 128 tiles (the chain links of the blocked
+//              algebra at small N: panel solves, K = 128 updates) is bound by one SM's DMMA rate per tile
+//              (128^3 flops = 17 us); a quarter of the tile per CTA and half of the work per warp spreads the
+//              same product over 4x the SMs.
+template <int WM, int WN, int STAGES, int MINB, int FM = 8>
 __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_nt_kernel(const GemmArgs g) {
-    constexpr int BM = 64 * WM, BN = 32 * WN, NT = WM * WN * 32;
+    constexpr int WROWS = 8 * FM;  // rows of a warp tile
+    constexpr int BM = WROWS * WM, BN = 32 * WN, NT = WM * WN * 32;
     constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;
     constexpr int RATIO = BM / BN > 0 ? BM / BN : 1;  // column tiles per diagonal block (BM >= BN)
 #if defined(GOGP_SIMT_HOST)
@@ -87,10 +93,10 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_nt_kernel(const Gemm
     }
     if (g.mtb > 0) {
         // tile of a block-cyclic local matrix that lies strictly above the global diagonal: nothing to do
-        constexpr int CPB = 128 / BN;  // column tiles per 128 columns (BM is always 128)
-        const int tbn = g.mtb * CPB;
-        const int I = g.mr0 + g.mpr * (ti / g.mtb), J = g.mc0 + g.mpc * (tj / tbn);
-        if (J > I || (J == I && (tj % tbn) * BN > (ti % g.mtb) * BM + BM - 1)) return;
+        constexpr int CPB = 128 / BN, RPB = 128 / BM;  // column / row tiles per 128 (the mask counts 128-tiles)
+        const int tbn = g.mtb * CPB, tbm = g.mtb * RPB;
+        const int I = g.mr0 + g.mpr * (ti / tbm), J = g.mc0 + g.mpc * (tj / tbn);
+        if (J > I || (J == I && (tj % tbn) * BN > (ti % tbm) * BM + BM - 1)) return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WN, wn = warp % WN;
@@ -119,9 +125,9 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_nt_kernel(const Gemm
         }
     };
 
-    double acc[8][4][2];
+    double acc[FM][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < FM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -140,17 +146,17 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_nt_kernel(const Gemm
             if (nxt < nk) load_stage(nxt % STAGES, nxt);
             cp_async_commit();
         }
-        const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * 64 + fr) * PITCH + fk;
+        const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * WROWS + fr) * PITCH + fk;
         const double* sb = smem + (kt % STAGES) * STAGE_DOUBLES + BM * PITCH + (wn * 32 + fr) * PITCH + fk;
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ++ks) {
-            double a[8], b[4];
+            double a[FM], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = sa[i * 8 * PITCH + ks * 4];
+            for (int i = 0; i < FM; ++i) a[i] = sa[i * 8 * PITCH + ks * 4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) b[j] = sb[j * 8 * PITCH + ks * 4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < FM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
@@ -167,9 +173,9 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_nt_kernel(const Gemm
         Cb = g.C + row0 * g.ldc + col0;
         ldc = g.ldc;
     }
-    const int er = wm * 64 + fr, ec = wn * 32 + 2 * fk;
+    const int er = wm * WROWS + fr, ec = wn * 32 + 2 * fk;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < FM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             double2* p = reinterpret_cast<double2*>(Cb + (int64_t)(er + i * 8) * ldc + ec + j * 8);

@@ -84,7 +84,8 @@ struct CudaGridBackend {
     std::vector<double> ts, tn;  // natural-scale parameters of the evaluation in flight
     int* dInfo = nullptr;
     double* dTmp = nullptr;       // reductions: max(block, 8) doubles
-    double* dTraceScr = nullptr;  // (block/128)^2 (nts + 1) doubles
+    double* dTraceScr = nullptr;  // per-tile partial sums of the trace: (local tiles) (nts + 1) doubles
+    int64_t traceScrCap = 0;
     double* hPin = nullptr;       // 64 doubles + room for alpha read-back is allocated by the caller
     int64_t hPinCap = 0;
     int64_t block = 0;
@@ -219,6 +220,18 @@ struct CudaGridBackend {
                      int64_t cols, double* accp, int qi) {
         ckg(gogp_dev_trace_block(h, ts.data(), alpha, kinv, ld, row0, rows, col0, cols, accp, dTraceScr, q[qi]));
     }
+    void trace_local(const double* alpha, const double* kinv, int64_t ld, int64_t rows, int64_t cols, const BcMask& mk,
+                     double* accp, int qi) {
+        const int64_t need = (rows / TILE) * (cols / TILE) * (nts + 1);
+        if (need > traceScrCap) {  // first evaluation after set_data: before any collective of the trace phase
+            free(dTraceScr);
+            dTraceScr = alloc(need);
+            traceScrCap = dTraceScr ? need : 0;
+            if (!dTraceScr) return;
+        }
+        ckg(gogp_dev_trace_local(h, ts.data(), alpha, kinv, ld, rows, cols, mk.tb, mk.r0, mk.pr, mk.c0, mk.pc, accp,
+                                 dTraceScr, q[qi]));
+    }
     void info_reset(int qi) { ck(cudaMemsetAsync(dInfo, 0, sizeof(int), q[qi]), "memset"); }
     void info_to(double* dst, int qi) { int_to_double_kernel<<<1, 1, 0, q[qi]>>>(dInfo, dst); }
     int info_host() {
@@ -324,7 +337,8 @@ gogp_status rank_create(GridRank& r, int ndim, const gogp_op* simil, int n_simil
     be.ck(cudaMalloc(&be.dInfo, sizeof(int)), "cudaMalloc");
     const int64_t tmpn = block > 8 ? block : 8;
     be.dTmp = be.alloc(tmpn);
-    be.dTraceScr = be.alloc((block / TILE) * (block / TILE) * (nts + 1));
+    be.traceScrCap = (block / TILE) * (block / TILE) * (nts + 1);
+    be.dTraceScr = be.alloc(be.traceScrCap);
     if (be.st != GOGP_OK) return be.st;
     if (world > 1) {
         NcclApi* api = nccl();

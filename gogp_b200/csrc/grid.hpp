@@ -445,9 +445,9 @@ struct BlockCyclic {
     void trace(double* out) {
         cur_phase = GP_TRACE;
         be.zero(gacc, nts + 1, GQ_MAIN);
-        for (int i = 0; i < nr; ++i)
-            for (int j = 0; j < nc && gcol(j) <= grow(i); ++j)
-                be.trace_block(alpha, blk(i, j), ld, (int64_t)grow(i) * NB, NB, (int64_t)gcol(j) * NB, NB, gacc, GQ_MAIN);
+        // one launch over the local matrix: the kernel maps a local tile to its global position and skips the blocks
+        // above the global diagonal (they hold V)
+        if (nr > 0 && nc > 0) be.trace_local(alpha, M, ld, (int64_t)nr * NB, (int64_t)nc * NB, mask_at(0, 0), gacc, GQ_MAIN);
         comm_begin();
         be.allreduce_sum(gacc, nts + 1, GQ_MAIN);
         comm_end();

@@ -45,6 +45,14 @@ void launch_grad_trace(const DevProgram& prog, const double* Xt, const double* a
 void launch_grad_trace_block(const DevProgram& prog, const double* Xt, int64_t ldx, const double* alpha,
                              const double* kinv, int64_t ld, int64_t N, int D, int64_t grow0, int rtiles,
                              int64_t gcol0, int ctiles, double* partial, double* out, cudaStream_t s);
+// The same trace in ONE launch over a rank's whole local matrix of a pr x pc block-cyclic distribution (grid.hpp):
+// rtiles x ctiles tiles at kinv (ld), tb tiles per distribution block, the first local block row / column being
+// global block r0 / c0.  out[0..ntheta] is ACCUMULATED into; partial: rtiles * ctiles * (ntheta+1) doubles.
+void launch_grad_trace_bc(const DevProgram& prog, const double* Xt, int64_t ldx, const double* alpha,
+                          const double* kinv, int64_t ld, int64_t N, int D, int rtiles, int ctiles, int tb, int r0, int pr,
+                          int c0, int pc, double* partial, double* out, cudaStream_t s);
+// dynamic shared memory the trace kernels need for a descriptor (checked against the 227 KB opt-in limit at create)
+size_t grad_trace_smem_bytes(int ndim, int ntheta);
 // Input gradient for Observe's with_obs layout (gp/gp.go:118-129, 488-493):
 //   gx[i*D+d] = sum_{j != i} W_ij d k(x_i, x_j)/d x_{i,d}
 void launch_grad_inputs(const DevProgram& prog, const double* Xt, const double* alpha, const double* kinv,

@@ -122,6 +122,63 @@ GOGP_HD void factor_dlog_theta(const DevFactor& f, double xa, double xb, double&
     }
 }
 
+// 1 / t for t >= 1 (the Matern polynomials): the hardware reciprocal + Newton steps, without the slow path of a
+// general FP64 division
+GOGP_HD double rcp_pos(double t) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(t);
+#else
+    return 1.0 / t;
+#endif
+}
+
+// Value and theta log-derivatives of one factor in one go: the gradient trace needs both, and they share their
+// transcendental (one sincos + one exp for Periodic, one exp for the Materns).  Values exactly as factor_value.
+GOGP_HD void factor_value_dlog(const DevProgram& prog, const DevFactor& f, double xa, double xb, double& val, double& g0,
+                               double& g1) {
+    g1 = 0.0;
+    switch (f.kind) {
+        case F_EVENTS:
+            val = events_value(prog, xa, xb);
+            g0 = 0.0;
+            return;
+        case F_PARAM:
+            val = f.a0;
+            g0 = 1.0;
+            return;
+        case F_NORMAL: {
+            const double d = (xa - xb) * f.i0;
+            val = exp(-d * d / 2);
+            g0 = d * d;
+            return;
+        }
+        case F_PERIODIC: {
+            const double u = fabs(xa - xb) * f.i1;
+            double sn, cs;
+            sincos(u, &sn, &cs);
+            const double d = sn * f.i0;
+            val = exp(-2 * d * d);
+            g0 = 4 * d * d;
+            g1 = 4 * d * cs * u * f.i0;
+            return;
+        }
+        case F_MATERN32: {
+            const double d = fabs(xa - xb) * f.i0;
+            const double t = 1 + GOGP_SQRT3 * d;
+            val = t * exp(-GOGP_SQRT3 * d);
+            g0 = 3 * d * d * rcp_pos(t);
+            return;
+        }
+        default: {  // F_MATERN52
+            const double d = fabs(xa - xb) * f.i0;
+            const double t = 1 + GOGP_SQRT5 * d + f.c * d * d;
+            val = t * exp(-GOGP_SQRT5 * d);
+            g0 = d * d * (5 - 2 * f.c + GOGP_SQRT5 * f.c * d) * rcp_pos(t);
+            return;
+        }
+    }
+}
+
 // (d f / d xa) / f ;  d/d xb is its negative for every stock (stationary) leaf.
 GOGP_HD double factor_dlog_xa(const DevFactor& f, double xa, double xb) {
     double r = xa - xb;

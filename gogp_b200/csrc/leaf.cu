@@ -272,18 +272,14 @@ __global__ void __launch_bounds__(256) trmv_kernel(const double* __restrict__ L,
 // forward substitution through shared memory.
 __global__ void __launch_bounds__(TILE) tile_inverse_kernel(const double* __restrict__ L, int64_t ld,
                                                             double* __restrict__ winv) {
-    extern __shared__ double sh[];  // T [128][129], then W column-major [128][129]
-    double* T = sh;
-    double* W = sh + TILE * (TILE + 1);
+    extern __shared__ double W[];  // column-major [128][129]: thread c owns column c
     const int t = blockIdx.x, c = threadIdx.x;
-    const double* Lt = L + (int64_t)t * TILE * ld + (int64_t)t * TILE;
-    for (int r = 0; r < TILE; ++r) T[r * (TILE + 1) + c] = c <= r ? Lt[(int64_t)r * ld + c] : 0.0;
-    __syncthreads();
+    const double* Lt = L + (int64_t)t * TILE * ld + (int64_t)t * TILE;  // rows are read by all threads at once: broadcast
     double* wc = W + c * (TILE + 1);
     for (int i = 0; i < TILE; ++i) {
         double s = i == c ? 1.0 : 0.0;
-        for (int k = c; k < i; ++k) s = fma(-T[i * (TILE + 1) + k], wc[k], s);
-        wc[i] = i >= c ? s / T[i * (TILE + 1) + i] : 0.0;
+        for (int k = c; k < i; ++k) s = fma(-Lt[(int64_t)i * ld + k], wc[k], s);
+        wc[i] = i >= c ? s / Lt[(int64_t)i * ld + i] : 0.0;
     }
     __syncthreads();
     double* out = winv + (int64_t)t * TILE * TILE;
@@ -457,7 +453,7 @@ void launch_trmv_lower(const double* L, int64_t ld, const double* v, double* out
 
 void launch_tile_inverse(const double* L, int64_t ld, double* winv, int tiles, cudaStream_t s) {
     if (tiles <= 0) return;
-    const size_t smem = (size_t)2 * TILE * (TILE + 1) * sizeof(double);
+    const size_t smem = (size_t)TILE * (TILE + 1) * sizeof(double);
     static std::atomic<bool> configured[64];
     int dev = 0;
     cudaGetDevice(&dev);

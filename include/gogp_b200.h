@@ -267,6 +267,12 @@ gogp_status gogp_dev_trtri_t(gogp_handle* h, const double* L, int64_t ld, int64_
 gogp_status gogp_dev_trace_block(gogp_handle* h, const double* theta_simil, const double* alpha, const double* kinv,
                                  int64_t ld, int64_t row0, int64_t rows, int64_t col0, int64_t cols, double* acc,
                                  double* scratch, void* stream);
+/* The same trace in ONE launch over a rank's whole local matrix (rows x cols at kinv, ld) of a pr x pc
+ * block-cyclic distribution with tb x tb tiles per block, the first local block row / column being global block
+ * r0 / c0; blocks above the global diagonal are skipped.  scratch: (rows/128)(cols/128)(ntheta_simil+1) doubles. */
+gogp_status gogp_dev_trace_local(gogp_handle* h, const double* theta_simil, const double* alpha, const double* kinv,
+                                 int64_t ld, int64_t rows, int64_t cols, int tb, int r0, int pr, int c0, int pc,
+                                 double* acc, double* scratch, void* stream);
 /* Host arithmetic on the (input-independent) noise program: variance and d variance / d log theta_n
  * at natural-scale theta_noise; the noise gradient is 0.5 tr(W) dlog[q] (gp/gp.go:133-150). */
 gogp_status gogp_noise_eval(gogp_handle* h, const double* theta_noise, double* variance, double* dlog);

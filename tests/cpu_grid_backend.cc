@@ -200,6 +200,17 @@ struct HostGridBackend {
                 }
             }
     }
+    void trace_local(const double* alpha, const double* kinv, int64_t ld, int64_t rows, int64_t cols, const BcMask& mk,
+                     double* accp, int q) {
+        // tile by tile with the kernel's mapping (cov_kernels.cuh trace_tile, mode 2)
+        for (int64_t ti = 0; ti < rows / 128; ++ti)
+            for (int64_t tj = 0; tj < cols / 128; ++tj) {
+                const int64_t row0 = ((mk.r0 + mk.pr * (ti / mk.tb)) * mk.tb + ti % mk.tb) * 128;
+                const int64_t col0 = ((mk.c0 + mk.pc * (tj / mk.tb)) * mk.tb + tj % mk.tb) * 128;
+                if (col0 > row0 + 127) continue;
+                trace_block(alpha, kinv + ti * 128 * ld + tj * 128, ld, row0, 128, col0, 128, accp, q);
+            }
+    }
     void info_reset(int) { info = 0; }
     void info_to(double* dst, int) { *dst = (double)info; }
     int info_host() { return info; }

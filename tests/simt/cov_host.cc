@@ -80,12 +80,36 @@ int simt_cov_build(const gogp_op* ops, int nops, int ntheta, int ndim, const dou
     return 2;
 }
 
-// out[ntheta + 1] = the fused trace over the whole matrix (kinv: strictly-lower tiles, kdiag: diagonal tiles)
-// or, with block = 1, over the rows x cols block at (row0, col0) of the same matrix given as one dense array
-// (kdiag ignored), accumulated into out.
+// The specialised trace kernel's instantiation for a program (mirrors trace_fast_shape of csrc/cov.cu)
+static bool trace_shape(const DevProgram& prog, int* nn_out, int* maxr_out) {
+    static const int inst[] = {8, 4, 3, 2, 1, 0};
+    for (int nn : inst) {
+        if (nn > 0 && (prog.nterms != 1 || prog.nnorm[0] < nn)) continue;
+        int worst = 0;
+        for (int t = 0; t < prog.nterms; ++t) {
+            int rest = 0;
+            for (int fi = prog.fbeg[t] + nn; fi < prog.fbeg[t + 1]; ++fi)
+                if (prog.f[fi].kind != F_PARAM) ++rest;
+            if (rest > worst) worst = rest;
+        }
+        if (worst > kTraceMaxRest) continue;
+        *nn_out = nn;
+        *maxr_out = worst == 0 ? 0 : (worst == 1 ? 1 : kTraceMaxRest);
+        return true;
+    }
+    return false;
+}
+
+// out[ntheta + 1] = the fused trace.  block = 0: over the whole matrix (kinv: strictly-lower tiles, kdiag: diagonal
+// tiles); block = 1: over the rows x cols block at (row0, col0) of the same matrix given as one dense array (kdiag
+// ignored), accumulated into out; block = 2: kinv is ONE RANK's local matrix (rows x cols, ld = cols) of a
+// pr x pc block-cyclic distribution with tb tiles per block whose first block row / column is global block
+// row0 / col0 (bc = {tb, pr, pc}), accumulated into out.  fast: 0 the interpreted kernel, 1 the specialised one
+// (returns 2 when the program has no fast shape).
 int simt_grad_trace(const gogp_op* ops, int nops, int ntheta, int ndim, const double* theta, const double* events,
                     int nev, const double* X, int64_t N, const double* alpha, const double* kinv, const double* kdiag,
-                    int block, int64_t row0, int64_t rows, int64_t col0, int64_t cols, double* out) {
+                    int block, int64_t row0, int64_t rows, int64_t col0, int64_t cols, const int* bc, int fast,
+                    double* out) {
     Problem p;
     if (!setup(p, ops, nops, ntheta, ndim, theta, events, nev, X, N)) return 1;
     const DevProgram& prog = p.prog;
@@ -94,28 +118,59 @@ int simt_grad_trace(const gogp_op* ops, int nops, int ntheta, int ndim, const do
     const int64_t Npad = p.Npad;
     const size_t smem = (size_t)2 * D * TILE * sizeof(double) + 16 + (size_t)2 * GT_E * 256 * sizeof(double) +
                         (size_t)(prog.ntheta + 1) * 256 * sizeof(double);
+    TraceMap map{};
     int ntiles;
-    std::vector<double> partial;
-    if (!block) {
+    const double* base = kinv;
+    int64_t ld = Npad;
+    if (block == 0) {
         const int T = (int)(Npad / TILE);
         ntiles = T * (T + 1) / 2;
-        partial.assign((size_t)ntiles * (prog.ntheta + 1), 0.0);
-        double* pp = partial.data();
-        simt::launch((unsigned)ntiles, 256, smem,
-                     [&] { grad_trace_kernel(prog, Xt, Npad, alpha, kinv, Npad, kdiag, N, D, pp, 0, 0, 0); });
+        map.mode = 0;
+    } else if (block == 1) {
+        const int rt = (int)(rows / TILE), ct = (int)(cols / TILE);
+        ntiles = rt * ct;
+        map.mode = 1;
+        map.ctiles = ct;
+        map.grow0 = row0;
+        map.gcol0 = col0;
+        base = kinv + row0 * Npad + col0;
+        kdiag = nullptr;
     } else {
         const int rt = (int)(rows / TILE), ct = (int)(cols / TILE);
         ntiles = rt * ct;
-        partial.assign((size_t)ntiles * (prog.ntheta + 1), 0.0);
-        double* pp = partial.data();
-        const double* blk = kinv + row0 * Npad + col0;
-        simt::launch((unsigned)ntiles, 256, smem, [&] {
-            grad_trace_kernel(prog, Xt, Npad, alpha, blk, Npad, nullptr, N, D, pp, ct, row0, col0);
-        });
+        map.mode = 2;
+        map.ctiles = ct;
+        map.tb = bc[0];
+        map.r0 = (int)row0;
+        map.pr = bc[1];
+        map.c0 = (int)col0;
+        map.pc = bc[2];
+        ld = cols;
+        kdiag = nullptr;
     }
-    const double* pp = partial.data();
+    std::vector<double> partial((size_t)ntiles * (prog.ntheta + 1), 0.0);
+    double* pp = partial.data();
+    if (!fast) {
+        simt::launch((unsigned)ntiles, 256, smem,
+                     [&] { grad_trace_kernel(prog, Xt, Npad, alpha, base, ld, kdiag, N, D, pp, map); });
+    } else {
+        int nn = -1, maxr = 0;
+        if (!trace_shape(prog, &nn, &maxr)) return 2;
+        bool done = false;
+#define CASE(NNV, MR)                                                                                       \
+    if (!done && nn == NNV && maxr == MR) {                                                                 \
+        simt::launch((unsigned)ntiles, 256, smem, [&] {                                                     \
+            grad_trace_fast_kernel<NNV, MR, 1>(prog, Xt, Npad, alpha, base, ld, kdiag, N, D, pp, map);      \
+        });                                                                                                 \
+        done = true;                                                                                        \
+    }
+        CASE(0, 0) CASE(0, 1) CASE(0, 4) CASE(1, 0) CASE(1, 1) CASE(1, 4) CASE(2, 0) CASE(2, 1) CASE(2, 4)
+        CASE(3, 0) CASE(3, 1) CASE(3, 4) CASE(4, 0) CASE(4, 1) CASE(4, 4) CASE(8, 0) CASE(8, 1) CASE(8, 4)
+#undef CASE
+        if (!done) return 2;
+    }
     const int nslots = prog.ntheta + 1;
-    simt::launch((unsigned)nslots, 256, 0, [&] { grad_reduce_kernel(pp, ntiles, nslots, out, block); });
+    simt::launch((unsigned)nslots, 256, 0, [&] { grad_reduce_kernel(pp, ntiles, nslots, out, block != 0); });
     return 0;
 }
 

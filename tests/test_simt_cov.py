@@ -26,7 +26,8 @@ def simt():
     L = C.CDLL(so)
     head = [C.POINTER(Op), C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp, C.c_int64]   # descriptor, theta, events, X, N
     L.simt_cov_build.argtypes = head + [C.c_double, C.c_int, dp]
-    L.simt_grad_trace.argtypes = head + [dp, dp, dp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, dp]
+    L.simt_grad_trace.argtypes = head + [dp, dp, dp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                         C.POINTER(C.c_int), C.c_int, dp]
     L.simt_grad_inputs.argtypes = head + [dp, dp, dp, dp]
     for f in (L.simt_cov_build, L.simt_grad_trace, L.simt_grad_inputs):
         f.restype = C.c_int
@@ -81,8 +82,11 @@ def test_build_kernels_on_the_emulator(simt, name, fast_expected):
         assert np.array_equal(np.nan_to_num(fast, nan=-1.0), np.nan_to_num(out, nan=-1.0))
 
 
-@pytest.mark.parametrize("name", ["c2_rbf", "c3_ard3", "hyperpriors", "events"])
-def test_trace_kernel_on_the_emulator(simt, name):
+@pytest.mark.parametrize("name", ["c2_rbf", "c3_ard3", "hyperpriors", "events", "c5_matern4", "c3_ard8", "sum_times"])
+@pytest.mark.parametrize("fast", [0, 1])
+def test_trace_kernel_on_the_emulator(simt, name, fast):
+    """fast = 0: the descriptor interpreter; fast = 1: the specialised kernel (Normal factors unrolled, value and
+    log-derivatives of the other leaves evaluated together, everything in registers)."""
     N = 200
     og, args, keep, nts, ndim, _ = _problem(name, N, seed=4)
     Npad, T = 256, 2
@@ -96,7 +100,7 @@ def test_trace_kernel_on_the_emulator(simt, name):
     kinv[128:, :128] = dense[128:, :128]
     kdiag = np.stack([dense[t * 128:(t + 1) * 128, t * 128:(t + 1) * 128] for t in range(T)]).copy()
     out = np.zeros(nts + 1)
-    assert simt.simt_grad_trace(*args, _p(alpha), _p(kinv), _p(kdiag), 0, 0, 0, 0, 0, _p(out)) == 0
+    assert simt.simt_grad_trace(*args, _p(alpha), _p(kinv), _p(kdiag), 0, 0, 0, 0, 0, None, fast, _p(out)) == 0
     scale = max(1.0, np.max(np.abs(gref)))
     assert np.max(np.abs(out[:nts] - gref)) <= 1e-10 * scale, (out[:nts], gref)
     trw = float(og.Alpha @ og.Alpha - np.trace(Kinv))
@@ -104,8 +108,49 @@ def test_trace_kernel_on_the_emulator(simt, name):
     # the block mode of the distributed path: the three lower 128-blocks, accumulated, give the same sums
     acc = np.zeros(nts + 1)
     for (r0, c0) in ((0, 0), (128, 0), (128, 128)):
-        assert simt.simt_grad_trace(*args, _p(alpha), _p(dense), None, 1, r0, 128, c0, 128, _p(acc)) == 0
+        assert simt.simt_grad_trace(*args, _p(alpha), _p(dense), None, 1, r0, 128, c0, 128, None, fast, _p(acc)) == 0
     assert np.max(np.abs(acc - out)) <= 1e-12 * max(1.0, np.max(np.abs(out)))
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("Pr,Pc,tb", [(2, 1, 1), (1, 2, 1), (2, 2, 1), (1, 1, 2), (2, 1, 2)])
+def test_trace_over_block_cyclic_local_matrices(simt, fast, Pr, Pc, tb):
+    """Mode 2 (grid.hpp's single trace launch per rank): every rank's local matrix of a Pr x Pc block-cyclic
+    distribution (blocks above the global diagonal poisoned) -- the ranks' sums add up to the whole trace."""
+    name, N = "c3_ard3", 500
+    og, args, keep, nts, ndim, _ = _problem(name, N, seed=6)
+    Npad, T = 512, 4
+    gref = og.gradient()[:nts]
+    Kinv = np.linalg.inv(og.K)
+    alpha = np.zeros(Npad)
+    alpha[:N] = og.Alpha
+    dense = np.eye(Npad)
+    dense[:N, :N] = Kinv
+    nb, NB = T // tb, 128 * tb
+    acc = np.zeros(nts + 1)
+    for r in range(Pr):
+        for c in range(Pc):
+            rows = [I for I in range(nb) if I % Pr == r]
+            cols = [J for J in range(nb) if J % Pc == c]
+            if not rows or not cols:
+                continue
+            local = np.full((len(rows) * NB, len(cols) * NB), np.nan)
+            for i, I in enumerate(rows):
+                for j, J in enumerate(cols):
+                    if J <= I:
+                        local[i * NB:(i + 1) * NB, j * NB:(j + 1) * NB] = dense[I * NB:(I + 1) * NB, J * NB:(J + 1) * NB]
+            if tb > 1:   # within a diagonal block the tiles above the diagonal must not be read either
+                for i, I in enumerate(rows):
+                    for j, J in enumerate(cols):
+                        if I == J:
+                            for a in range(tb):
+                                for b in range(a + 1, tb):
+                                    local[i * NB + a * 128:i * NB + (a + 1) * 128, j * NB + b * 128:j * NB + (b + 1) * 128] = np.nan
+            bc = (C.c_int * 3)(tb, Pr, Pc)
+            local = np.ascontiguousarray(local)
+            assert simt.simt_grad_trace(*args, _p(alpha), _p(local), None, 2, r, local.shape[0], c, local.shape[1], bc,
+                                        fast, _p(acc)) == 0
+    assert np.max(np.abs(acc[:nts] - gref)) <= 1e-10 * max(1.0, np.max(np.abs(gref))), (acc[:nts], gref)
 
 
 def test_input_gradient_kernel_on_the_emulator(simt):

@@ -51,7 +51,7 @@ def _tiles(M, t=128):
     return M.reshape(M.shape[0] // t, t, M.shape[1] // t, t).swapaxes(1, 2)
 
 
-@pytest.mark.parametrize("shape", [0, 1])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3])
 def test_full_rectangular_update(gemm, shape):
     rng = np.random.default_rng(shape)
     m, n, k = 256, 128, 256
@@ -62,7 +62,7 @@ def test_full_rectangular_update(gemm, shape):
     assert np.abs(Cm - ref).max() <= 1e-13 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("shape", [0, 1])
+@pytest.mark.parametrize("shape", [0, 1, 2])
 def test_lower_tiles_only_syrk(gemm, shape):
     rng = np.random.default_rng(10 + shape)
     n, k = 256, 128
@@ -71,11 +71,28 @@ def test_lower_tiles_only_syrk(gemm, shape):
     C0 = Cm.copy()
     gemm.simt_dgemm(_p(Cm), n, _p(A), k, _p(A), k, n, n, k, -1.0, 1.0, LOWER, None, shape)
     ref = C0 - A @ A.T
-    T, Tc, Tr = _tiles(Cm), _tiles(C0), _tiles(ref)
-    for i in range(2):
-        for j in range(2):
+    t = 64 if shape == 2 else 128                            # the latency shape walks 64 x 64 tiles
+    T, Tc, Tr = _tiles(Cm, t), _tiles(C0, t), _tiles(ref, t)
+    for i in range(n // t):
+        for j in range(n // t):
             want = Tr[i, j] if j <= i else Tc[i, j]          # tiles above the diagonal are not touched
             assert np.abs(T[i, j] - want).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_latency_shape_triangular_k_range(gemm):
+    """U12 = -U11 L21^T (Blocked::trtri_t) with the 64 x 64 shape: A upper triangular w.r.t. its own origin, the k
+    range of a 64-row tile starts at its first row; what lies below the diagonal inside A is never read."""
+    rng = np.random.default_rng(21)
+    m, n = 256, 128
+    U = np.triu(rng.standard_normal((m, m)))
+    Up = U.copy()
+    for t in range(m // 64):                                 # poison everything left of each 64-row tile's k range
+        Up[t * 64:(t + 1) * 64, :t * 64] = np.nan
+    L21 = rng.standard_normal((n, m))
+    Cm = np.full((m, n), np.nan)
+    gemm.simt_dgemm(_p(Cm), n, _p(Up), m, _p(L21), m, m, n, m, -1.0, 0.0, KTRI, None, 2)
+    ref = -U @ L21.T
+    assert np.abs(Cm - ref).max() <= 1e-13 * np.abs(ref).max()
 
 
 def test_triangular_k_range_and_diagonal_tiles_to_side_buffer(gemm):
@@ -108,6 +125,11 @@ def test_in_place_solve_with_a_diagonal_block(gemm):
     view = Bm[:, 128:256]
     ptr = C.cast(Bm.ctypes.data + 128 * 8, dp)
     gemm.simt_dgemm(ptr, 384, ptr, 384, _p(W), 128, m, 128, 128, 1.0, 0.0, INPLACE, None, 0)
+    assert np.abs(view - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.array_equal(Bm[:, :128], keep[:, :128]) and np.array_equal(Bm[:, 256:], keep[:, 256:])
+    # the 32 x 128 latency shape: eight CTAs, each owning 32 whole rows
+    Bm[:] = keep
+    gemm.simt_dgemm(ptr, 384, ptr, 384, _p(W), 128, m, 128, 128, 1.0, 0.0, INPLACE, None, 3)
     assert np.abs(view - ref).max() <= 1e-13 * np.abs(ref).max()
     assert np.array_equal(Bm[:, :128], keep[:, :128]) and np.array_equal(Bm[:, 256:], keep[:, 256:])
 
