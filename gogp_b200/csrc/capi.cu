@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler is attached
+
 #include "../../include/gogp_b200.h"
 #include "blocked.hpp"
 #include "kernels.h"
@@ -480,7 +482,9 @@ gogp_status absorb(gogp_handle* h) {
 
     CK(cudaMemsetAsync(h->dInfo, 0, sizeof(int), s));
     CK(cudaEventRecord(h->ev[0], s));
+    nvtxRangePushA("gogp:build");
     launch_cov_build(prog, h->dXt, N, Npad, h->ndim, h->noise_var, h->dA, s);
+    nvtxRangePop();
     ++h->launches;
     CK(cudaEventRecord(h->ev[1], s));
 
@@ -492,14 +496,18 @@ gogp_status absorb(gogp_handle* h) {
         for (auto& l : h->la) l.pending = l.below_pending = false;
         be.la = h->la;
     }
+    nvtxRangePushA("gogp:potrf");
     bl.potrf_la(0, Npad, 0);
+    nvtxRangePop();
     CK(cudaEventRecord(h->ev[2], s));
 
     // alpha = L^-T (L^-1 y)
+    nvtxRangePushA("gogp:solve");
     CK(cudaMemcpyAsync(h->dW, h->dY, (size_t)Npad * sizeof(double), cudaMemcpyDeviceToDevice, s));
     launch_trsv_lower(h->dA, Npad, h->dWinv, h->dW, h->dZ, Npad, false, s, &h->launches, h->dSync);
     launch_trsv_lower(h->dA, Npad, h->dWinv, h->dZ, h->dAlpha, Npad, true, s, &h->launches, h->dSync);
     launch_logdet_dot(h->dA, Npad, h->dY, h->dAlpha, N, h->dRed, s);
+    nvtxRangePop();
     ++h->launches;
     CK(cudaEventRecord(h->ev[3], s));
     gogp_status st = ensure_pin(h, 8);
@@ -758,6 +766,7 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
 
     CK(cudaEventRecord(h->ev[0], s));
     if (!h->have_kinv) {
+        nvtxRangePushA("gogp:potri");
         CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
         Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
         // per-launch accounting needs launches that do not overlap: profile on one stream
@@ -771,14 +780,17 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len) {
         }
         bl.lauum(h->dB, h->dDg, Npad);
         h->have_kinv = true;
+        nvtxRangePop();
     }
     CK(cudaEventRecord(h->ev[1], s));
+    nvtxRangePushA("gogp:trace");
     launch_grad_trace(prog, h->dXt, h->dAlpha, h->dB, h->dDg, N, Npad, D, h->dPartial, h->dRed, s);
     h->launches += 2;
     if (h->with_obs) {
         launch_grad_inputs(prog, h->dXt, h->dAlpha, h->dB, h->dDg, N, Npad, D, h->dGx, s);
         ++h->launches;
     }
+    nvtxRangePop();
     CK(cudaEventRecord(h->ev[2], s));
     const int64_t npin = (h->nts + 1) + (h->with_obs ? N * (D + 1) : 0);
     st = ensure_pin(h, npin + 8);
@@ -839,6 +851,7 @@ gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu,
     gogp_status st = ensure_pin(h, 3 * chunk + 8);
     if (st != GOGP_OK) return st;
     CK(cudaEventRecord(h->ev[6], s));
+    nvtxRangePushA("gogp:predict");
     for (int64_t m0 = 0; m0 < M; m0 += chunk) {
         const int64_t mc = (M - m0) < chunk ? (M - m0) : chunk;
         const int64_t mpad = pad_tile(mc);
@@ -872,6 +885,7 @@ gogp_status gogp_produce(gogp_handle* h, const double* Z, int64_t M, double* mu,
             sigma[m0 + i] = std::sqrt(rad > 0.0 ? rad : (rad == rad ? 0.0 : rad));  // clamp; NaN stays NaN
         }
     }
+    nvtxRangePop();
     CK(cudaEventRecord(h->ev[7], s));
     CK(cudaStreamSynchronize(s));
     float ms = 0.f;

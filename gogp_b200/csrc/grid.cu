@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cmath>
 #include <cstdio>
@@ -23,6 +24,7 @@
 #include "../../include/gogp_b200.h"
 #include "grid.hpp"
 #include "kernels.h"
+#include "peer_bcast.hpp"
 
 using namespace gogp;
 
@@ -33,6 +35,7 @@ struct NcclApi {
     void* lib = nullptr;
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitRankConfig) CommInitRankConfig = nullptr;  // optional
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclBroadcast) Broadcast = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
@@ -68,10 +71,14 @@ NcclApi* nccl() {
         GOGP_NCCL_SYM(GetErrorString)
         GOGP_NCCL_SYM(GetVersion)
 #undef GOGP_NCCL_SYM
+        api.CommInitRankConfig =
+            reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(lib, "ncclCommInitRankConfig"));
     });
     return api.err.empty() ? &api : nullptr;
 }
 const char* nccl_load_error() { return "NCCL is not available (libnccl.so.2 could not be bound; set GOGP_NCCL_LIB)"; }
+
+constexpr int kNcclMaxCtas = 0;  // default cap on the CTAs of a collective (see rank_create); 0: NCCL's choice
 
 __global__ void int_to_double_kernel(const int* src, double* dst) { *dst = (double)*src; }
 
@@ -96,6 +103,8 @@ struct CudaGridBackend {
     int64_t comm_bytes = 0, dev_bytes = 0;
     gogp_status st = GOGP_OK;  // first failure sticks; the orchestration runs on (every rank makes the same calls)
     std::string err;
+    PeerLink peer;                      // panel broadcasts by the copy engines over peer memory (peer_bcast.hpp)
+    size_t peer_min_bytes = 1u << 20;   // smaller messages stay on NCCL
 
     void fail(gogp_status s, const std::string& m) {
         if (st == GOGP_OK) {
@@ -232,6 +241,8 @@ struct CudaGridBackend {
         ckg(gogp_dev_trace_local(h, ts.data(), alpha, kinv, ld, rows, cols, mk.tb, mk.r0, mk.pr, mk.c0, mk.pc, accp,
                                  dTraceScr, q[qi]));
     }
+    void range_push(const char* name) { nvtxRangePushA(name); }  // NVTX: free unless a profiler is attached
+    void range_pop() { nvtxRangePop(); }
     void info_reset(int qi) { ck(cudaMemsetAsync(dInfo, 0, sizeof(int), q[qi]), "memset"); }
     void info_to(double* dst, int qi) { int_to_double_kernel<<<1, 1, 0, q[qi]>>>(dInfo, dst); }
     int info_host() {
@@ -243,6 +254,12 @@ struct CudaGridBackend {
     // ---- collectives (NCCL over NVLink), on the priority queue ---------------------------------------
     void bcast(double* p, int64_t n, int root, int qi) {
         if (world == 1 || n <= 0) return;
+        if (peer.usable(p, (size_t)n * 8, peer_min_bytes)) {
+            // every rank takes this branch together: the buffers, sizes and offsets are the same everywhere
+            if (!peer.bcast(p, (size_t)n * 8, root, q[qi])) fail(GOGP_NCCL_ERROR, peer.err);
+            if (rank != root) comm_bytes += 8 * n;
+            return;
+        }
         ckn(nccl()->Broadcast(p, p, (size_t)n, ncclDouble, root, comm, q[qi]), "ncclBroadcast");
         if (rank != root) comm_bytes += 8 * n;
     }
@@ -273,6 +290,7 @@ struct GridRank {
 
 struct gogp_grid {
     std::vector<std::unique_ptr<GridRank>> ranks;  // the ranks this process drives
+    std::unique_ptr<PeerCtl> peer_ctl;             // rendezvous counters of the peer broadcast when the ranks are threads
     int ndim = 1, nts = 0, ntn = 0, world = 1, pr = 1, pc = 1;
     int64_t block = 2048;
     std::string err;
@@ -314,7 +332,7 @@ gogp_status run_all(gogp_grid* g, F f) {
 
 gogp_status rank_create(GridRank& r, int ndim, const gogp_op* simil, int n_simil_ops, int nts, const gogp_op* noise,
                         int n_noise_ops, int ntn, int device, int rank, int world, int64_t block,
-                        const unsigned char* id) {
+                        const unsigned char* id, PeerCtl* shared_ctl) {
     CudaGridBackend& be = r.be;
     be.dev = device;
     be.rank = rank;
@@ -349,16 +367,43 @@ gogp_status rank_create(GridRank& r, int ndim, const gogp_op* simil, int n_simil
         ncclUniqueId uid;
         static_assert(sizeof(uid) == GOGP_GRID_ID_BYTES, "ncclUniqueId is 128 bytes");
         std::memcpy(&uid, id, sizeof(uid));
-        be.ckn(api->CommInitRank(&be.comm, world, uid, rank), "ncclCommInitRank");
+        // The collectives share the GPU with the DMMA GEMMs of the side queue: every CTA NCCL holds (mostly spinning
+        // on a peer whose panel is not ready yet) is an SM the trailing update cannot use.  The panels are tens of
+        // MB per step against tens of ms of GEMMs, so a few CTAs of copy bandwidth are plenty: cap them
+        // (GOGP_NCCL_MAX_CTAS, 0 = NCCL's own choice).
+        static const int max_ctas = getenv("GOGP_NCCL_MAX_CTAS") ? atoi(getenv("GOGP_NCCL_MAX_CTAS")) : kNcclMaxCtas;
+        if (max_ctas > 0 && api->CommInitRankConfig) {
+            ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+            cfg.minCTAs = 1;
+            cfg.maxCTAs = max_ctas;
+            be.ckn(api->CommInitRankConfig(&be.comm, world, uid, rank, &cfg), "ncclCommInitRankConfig");
+        } else {
+            be.ckn(api->CommInitRank(&be.comm, world, uid, rank), "ncclCommInitRank");
+        }
+        // GOGP_PEER_BCAST=1: the panel broadcasts go over peer memory with the copy engines when every rank can map
+        // every other (peer_bcast.hpp).  Opt-in: verified on two GPUs (threads and processes) only; NCCL otherwise.
+        static const int peer_on = getenv("GOGP_PEER_BCAST") ? atoi(getenv("GOGP_PEER_BCAST")) : 0;
+        if (be.st == GOGP_OK && peer_on && be.peer.attach(shared_ctl, id, rank, world, device)) be.peer.setup_events();
     }
     return be.st;
+}
+
+// Teardown in two phases.  First, in parallel on every local rank: drain the streams and take the peer mappings down
+// (a rendezvous of the ranks).  Then, one rank after the other: free memory and destroy the communicator -- cudaFree
+// synchronises its device, and doing that on one thread while another is inside ncclCommDestroy is the kind of
+// concurrency NCCL warns against.
+void rank_quiesce(GridRank& r) {
+    CudaGridBackend& be = r.be;
+    cudaSetDevice(be.dev);
+    if (be.q[GQ_MAIN]) cudaStreamSynchronize(be.q[GQ_MAIN]);
+    if (be.q[GQ_SIDE]) cudaStreamSynchronize(be.q[GQ_SIDE]);
+    be.peer.unregister_memory();
+    be.peer.detach();
 }
 
 void rank_destroy(GridRank& r) {
     CudaGridBackend& be = r.be;
     cudaSetDevice(be.dev);
-    if (be.q[GQ_MAIN]) cudaStreamSynchronize(be.q[GQ_MAIN]);
-    if (be.q[GQ_SIDE]) cudaStreamSynchronize(be.q[GQ_SIDE]);
     if (r.inited) r.bc.release();
     if (be.comm && nccl()) nccl()->CommDestroy(be.comm);
     be.free(be.dTmp);
@@ -405,6 +450,7 @@ gogp_status rank_set_data(gogp_grid* g, GridRank& r, const double* X, const doub
     if (r.inited) {
         cudaStreamSynchronize(be.q[GQ_MAIN]);
         cudaStreamSynchronize(be.q[GQ_SIDE]);
+        be.peer.unregister_memory();
         r.bc.release();
         r.inited = false;
     }
@@ -441,6 +487,12 @@ gogp_status rank_set_data(gogp_grid* g, GridRank& r, const double* X, const doub
     if (all != GOGP_OK && r.inited) {
         r.bc.release();
         r.inited = false;
+    }
+    if (all == GOGP_OK && be.world > 1 && be.peer.events_ok) {
+        // the buffers the big broadcasts live in: the two panel generations and the diagonal-block staging
+        void* ptrs[3] = {r.bc.panel[0], r.bc.panel[1], r.bc.dk};
+        const size_t sizes[3] = {(size_t)r.bc.nb * r.bc.bsz * 8, (size_t)r.bc.nb * r.bc.bsz * 8, (size_t)r.bc.dk_len() * 8};
+        be.peer.register_memory(ptrs, sizes, 3);
     }
     return all;
 }
@@ -531,7 +583,7 @@ gogp_status gogp_grid_create_rank(int ndim, const gogp_op* simil, int n_simil_op
     g->block = block;
     g->ranks.emplace_back(new GridRank());
     const gogp_status s = rank_create(*g->ranks[0], ndim, simil, n_simil_ops, ntheta_simil, noise, n_noise_ops,
-                                      ntheta_noise, device, rank, world, block, id);
+                                      ntheta_noise, device, rank, world, block, id, nullptr);
     if (s != GOGP_OK) g->err = g->ranks[0]->be.err;
     return s;
 }
@@ -556,6 +608,7 @@ gogp_status gogp_create_grid(int ndim, const gogp_op* simil, int n_simil_ops, in
         if (gogp_grid_unique_id(id) != GOGP_OK) return gfail(g, GOGP_NCCL_ERROR, nccl_load_error());
     }
     for (int i = 0; i < ndev; ++i) g->ranks.emplace_back(new GridRank());
+    g->peer_ctl.reset(new PeerCtl());  // value-initialised: all counters zero
     // ncclCommInitRank blocks until every rank has joined: one host thread per device
     std::vector<int> devs(devices, devices + ndev);
     return run_all(g, [&](GridRank& r) {
@@ -563,12 +616,16 @@ gogp_status gogp_create_grid(int ndim, const gogp_op* simil, int n_simil_ops, in
         for (size_t k = 0; k < g->ranks.size(); ++k)
             if (g->ranks[k].get() == &r) pos = (int)k;
         return rank_create(r, ndim, simil, n_simil_ops, ntheta_simil, noise, n_noise_ops, ntheta_noise, devs[pos], pos, ndev,
-                           block, id);
+                           block, id, g->peer_ctl.get());
     });
 }
 
 void gogp_grid_destroy(gogp_grid* g) {
     if (!g) return;
+    run_all(g, [&](GridRank& r) {
+        rank_quiesce(r);
+        return GOGP_OK;
+    });
     for (auto& r : g->ranks) rank_destroy(*r);
     delete g;
 }
@@ -650,6 +707,16 @@ gogp_status gogp_grid_stats(const gogp_grid* g, double* stats) {
     stats[5] = (double)r.be.dev_bytes;
     stats[6] = (double)ver;
     stats[7] = (double)g->world;
+    stats[8] = (double)r.be.peer.pulled_bytes;
+    // device time of the last Observe + Gradient: the slowest local rank's own sum of phases (the per-phase maxima of
+    // gogp_grid_phase_times do not add up when the ranks drift apart inside an evaluation)
+    double worst = 0.0;
+    for (const auto& rk : g->ranks) {
+        double sum = 0.0;
+        for (int p = 0; p < GOGP_GRID_NPHASE; ++p) sum += rk->bc.phase_ms[p];
+        if (sum > worst) worst = sum;
+    }
+    stats[9] = worst;
     return GOGP_OK;
 }
 

@@ -461,11 +461,17 @@ struct BlockCyclic {
         for (double& v : phase_ms) v = 0.0;
         for (double& v : comm_ms) v = 0.0;
         const int t0 = be.tic(GQ_MAIN);
+        be.range_push("gogp_grid:build");
         build();
+        be.range_pop();
         const int t1 = be.tic(GQ_MAIN);
+        be.range_push("gogp_grid:factor");
         factor();
+        be.range_pop();
         const int t2 = be.tic(GQ_MAIN);
+        be.range_push("gogp_grid:solve");
         const bool ok = solve_lml(lml, bad_pivot);
+        be.range_pop();
         const int t3 = be.tic(GQ_MAIN);
         be.sync(GQ_MAIN);
         phase_ms[GP_BUILD] = be.toc(t0, t1);
@@ -479,11 +485,15 @@ struct BlockCyclic {
         spans.clear();
         be.tic_reset();
         const int t0 = be.tic(GQ_MAIN);
+        be.range_push("gogp_grid:sweep");
         if (!have_kinv) sweep();
+        be.range_pop();
         const int t1 = be.tic(GQ_MAIN);
+        be.range_push("gogp_grid:alpha+trace");
         solve_alpha();
         const int t2 = be.tic(GQ_MAIN);
         trace(out);
+        be.range_pop();
         const int t3 = be.tic(GQ_MAIN);
         be.sync(GQ_MAIN);
         phase_ms[GP_SWEEP] = be.toc(t0, t1);

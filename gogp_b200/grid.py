@@ -153,7 +153,7 @@ class GridGP:
         return dict(zip(_lib.GRID_PHASES, ms)), dict(zip(_lib.GRID_PHASES, cm))
 
     def Stats(self):
-        s = np.zeros(8)
+        s = np.zeros(12)
         _lib.lib().gogp_grid_stats(self._g, _lib.dptr(s))
-        return {"nccl_bytes_received": int(s[0]), "launches": int(s[1]), "pr": int(s[2]), "pc": int(s[3]),
-                "block": int(s[4]), "device_bytes": int(s[5]), "nccl_version": int(s[6]), "world": int(s[7])}
+        return {"peer_copy_bytes_received": int(s[8]), "collective_bytes_received": int(s[0]), "launches": int(s[1]), "pr": int(s[2]), "pc": int(s[3]),
+                "block": int(s[4]), "device_bytes": int(s[5]), "nccl_version": int(s[6]), "world": int(s[7]), "eval_ms": float(s[9])}

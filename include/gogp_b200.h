@@ -281,8 +281,10 @@ gogp_status gogp_noise_eval(gogp_handle* h, const double* theta_noise, double* v
  * (SURVEY.md section 8e / 8b `gogp_create_grid`; BASELINE configs[4], N = 131072.)  The covariance matrix no longer
  * fits one GPU: K is cut into block x block pieces dealt round-robin to a pr x pc process grid, every rank builds
  * its own pieces from the replicated inputs, and Observe / Gradient (gp/gp.go:374-413, 418-499) run as a
- * right-looking block Cholesky plus one fused pass for V = L^-T and K^-1 = V V^T, with NCCL broadcasts of the
- * panels over NVLink (gogp_b200/csrc/grid.hpp, grid.cu).  libnccl.so.2 is bound at the first grid call (dlopen:
+ * right-looking block Cholesky plus one fused pass for V = L^-T and K^-1 = V V^T.  The panels travel over NVLink
+ * peer memory, pulled by the copy engines so that no SM leaves the GEMMs (gogp_b200/csrc/peer_bcast.hpp; CUDA IPC
+ * between processes); the small reductions, and the panels too when a peer mapping is unavailable, go through NCCL
+ * (gogp_b200/csrc/grid.hpp, grid.cu).  libnccl.so.2 is bound at the first grid call (dlopen:
  * the copy already loaded in the process, e.g. PyTorch's, else the system one); a library without NCCL still
  * serves every single-GPU entry point, and a grid call then fails with GOGP_NCCL_ERROR.
  *
@@ -332,9 +334,11 @@ gogp_status gogp_grid_get_alpha(gogp_grid* g, double* alpha, int64_t N);
  * the part of each phase the priority stream spent inside NCCL calls (it includes waiting for peers). */
 gogp_status gogp_grid_phase_times(const gogp_grid* g, double* ms /* GOGP_GRID_NPHASE */,
                                   double* comm_ms /* GOGP_GRID_NPHASE or NULL */);
-/* stats[0] bytes received through NCCL by the first local rank since creation, [1] kernels launched by it,
- * [2] pr, [3] pc, [4] block, [5] bytes of device memory held by it, [6] NCCL version code. */
-gogp_status gogp_grid_stats(const gogp_grid* g, double* stats /* 8 */);
+/* stats[0] bytes received by the first local rank through collectives since creation, [1] kernels launched by it,
+ * [2] pr, [3] pc, [4] block, [5] bytes of device memory held by it, [6] NCCL version code, [7] ranks, [8] the part of
+ * [0] that was pulled over peer memory by the copy engines (panel broadcasts) instead of NCCL, [9] device
+ * milliseconds of the last Observe + Gradient on the slowest local rank (its own sum of phases). */
+gogp_status gogp_grid_stats(const gogp_grid* g, double* stats /* 12 */);
 const char* gogp_grid_last_error(const gogp_grid* g);
 
 /* Test/diagnostic access to device state: what = 0 K (before factorisation is

@@ -211,6 +211,8 @@ struct HostGridBackend {
                 trace_block(alpha, kinv + ti * 128 * ld + tj * 128, ld, row0, 128, col0, 128, accp, q);
             }
     }
+    void range_push(const char*) {}
+    void range_pop() {}
     void info_reset(int) { info = 0; }
     void info_to(double* dst, int) { *dst = (double)info; }
     int info_host() { return info; }

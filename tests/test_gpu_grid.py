@@ -100,7 +100,7 @@ def test_two_ranks_nccl_match_one_rank(grid):
     X, y, logt = cases.synth(name, N, seed=7)
     lml1, grad1, alpha1, _ = _grid_eval(name, X, y, logt, [0], block=NB)
     lml2, grad2, alpha2, st = _grid_eval(name, X, y, logt, [0, 1], grid=grid, block=NB)
-    assert st["world"] == 2 and st["nccl_bytes_received"] > 0 and (st["pr"], st["pc"]) == grid
+    assert st["world"] == 2 and st["collective_bytes_received"] > 0 and (st["pr"], st["pc"]) == grid
     assert abs(lml2 - lml1) <= 1e-11 * max(abs(lml1), N)
     assert np.max(np.abs(alpha2 - alpha1)) <= 1e-9 * max(1.0, np.max(np.abs(alpha1)))
     assert np.max(np.abs(grad2 - grad1)) <= 1e-9 * max(1.0, np.max(np.abs(grad1)))

@@ -65,6 +65,8 @@ def main():
     ap.add_argument("--restarts", type=int, default=64)
     ap.add_argument("--alg", default="adam", choices=["adam", "lbfgs"])
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--threshold", type=float, default=1e-4,
+                    help="gradient threshold (tutorial/tutorial.go:28 THRESHOLD = 1e-6 with ITERS = 1000)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -81,18 +83,21 @@ def main():
     starts = np.stack([priors.sample(rng) for _ in range(a.restarts)])
     starts[:, 2:4] = np.clip(starts[:, 2:4], -1.5, 1.5)   # keep the sampled length scales where K stays well conditioned
     evals = [0]
+    stats = []
 
     def optimise(x0):
         x = np.ascontiguousarray(x0, dtype=np.float64)
         try:
-            res = g.Optimize(x, alg=a.alg, iters=a.iters, threshold=1e-4, rate=0.05, priors=priors)
+            res = g.Optimize(x, alg=a.alg, iters=a.iters, threshold=a.threshold, rate=0.05, priors=priors)
         except Exception:  # a start where K is not positive definite: the restart is dropped
             return -np.inf, x0
         evals[0] += res["evals"]
+        stats.append((res["iters"], res["evals"], res["grads"], bool(res["converged"])))
         return res["lml"], x
 
     optimise(starts[0].copy())  # warm-up (allocations); not counted
     evals[0] = 0
+    del stats[:]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -117,7 +122,8 @@ def main():
     if rank == 0:
         print(json.dumps({
             "workload": "configs[3]: hyperpriors model, multi-start restarts sharded across GPUs (no collective)",
-            "N": a.n, "restarts": a.restarts, "n_gpus": world, "alg": a.alg, "iters": a.iters,
+            "N": a.n, "restarts": a.restarts, "n_gpus": world, "alg": a.alg, "iters": a.iters, "threshold": a.threshold,
+            "rank0_restarts": [{"iters": s_[0], "evals": s_[1], "grads": s_[2], "converged": s_[3]} for s_ in stats],
             "seconds": dt, "timing": "device time of each rank's share (CUDA events on its handle's stream), max over ranks",
             "wall_seconds": wall, "restarts_per_s": a.restarts / dt, "evaluations": total_evals,
             "evals_per_s_total": total_evals / dt, "best_restart": best, "best_objective": float(obj[best]),
