@@ -23,7 +23,7 @@ PHASES = ("upload", "build", "potrf", "solve", "potri", "trace", "predict")
 
 # every symbol include/gogp_b200.h declares
 SYMBOLS = (
-    "gogp_create", "gogp_destroy", "gogp_set_events", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_lml",
+    "gogp_create", "gogp_destroy", "gogp_set_events", "gogp_set_data", "gogp_observe", "gogp_gradient", "gogp_absorb", "gogp_extend", "gogp_lml",
     "gogp_produce", "gogp_optimize", "gogp_get_alpha", "gogp_get_factor", "gogp_set_state", "gogp_last_error", "gogp_status_string",
     "gogp_phase_times", "gogp_launch_count", "gogp_debug_fetch", "gogp_debug_build", "gogp_debug_fp64_peak",
     "gogp_debug_gemm", "gogp_debug_leaf", "gogp_debug_leaf_run", "gogp_dev_set_inputs", "gogp_dev_cov_block", "gogp_dev_potrf", "gogp_dev_trsm",
@@ -92,6 +92,8 @@ def lib():
     L.gogp_gradient.restype = C.c_int
     L.gogp_absorb.argtypes = [H, dp, dp, dp, dp, C.c_int64]
     L.gogp_absorb.restype = C.c_int
+    L.gogp_extend.argtypes = [H, dp, dp, C.c_int64, dp]
+    L.gogp_extend.restype = C.c_int
     L.gogp_lml.argtypes = [H, dp]
     L.gogp_lml.restype = C.c_int
     L.gogp_produce.argtypes = [H, dp, C.c_int64, dp, dp]

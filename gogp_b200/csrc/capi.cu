@@ -459,48 +459,13 @@ gogp_status cond_estimate(gogp_handle* h, double* cond) {
     return GOGP_OK;
 }
 
-// absorb (gp/gp.go:89-239): build K, factor, alpha; then LML (gp/gp.go:244-253).
-gogp_status absorb(gogp_handle* h) {
-    h->factored = false;
-    h->have_kinv = false;
-    for (double& m : h->phase_ms) m = 0.0;
-    if (!h->has_data) {  // gp.X was never assigned: len(gp.X) == 0, the prior (gp/gp.go:101-104)
-        h->N = 0;
-        h->Npad = 0;
-        h->has_data = true;
-    }
-    if (h->N == 0) {
-        h->lml = 0.0;
-        h->factored = true;
-        h->have_lml = true;
-        return GOGP_OK;
-    }
+// Second half of absorb, shared with gogp_extend: alpha = K^-1 y (gp/gp.go:232-236), log det and y.alpha
+// (gp/gp.go:250-251), the pivot check of the factorisation queued before it (ev[1]..ev[2] bracket it), the LML and the
+// condition estimate.
+gogp_status finish_solve(gogp_handle* h) {
     const int64_t N = h->N, Npad = h->Npad;
     cudaStream_t s = h->stream;
-    DevProgram prog;
-    h->simil.bind(h->theta_s.data(), &prog);
-
-    CK(cudaMemsetAsync(h->dInfo, 0, sizeof(int), s));
-    CK(cudaEventRecord(h->ev[0], s));
-    nvtxRangePushA("gogp:build");
-    launch_cov_build(prog, h->dXt, N, Npad, h->ndim, h->noise_var, h->dA, s);
-    nvtxRangePop();
-    ++h->launches;
-    CK(cudaEventRecord(h->ev[1], s));
-
-    CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
-    Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
-    // per-launch accounting needs launches that do not overlap: profile on one stream
-    la_blocks(bl.la_nb);
-    if (!h->prof.on) {
-        for (auto& l : h->la) l.pending = l.below_pending = false;
-        be.la = h->la;
-    }
-    nvtxRangePushA("gogp:potrf");
-    bl.potrf_la(0, Npad, 0);
-    nvtxRangePop();
-    CK(cudaEventRecord(h->ev[2], s));
-
+    gogp_status st = GOGP_OK;
     // alpha = L^-T (L^-1 y)
     nvtxRangePushA("gogp:solve");
     CK(cudaMemcpyAsync(h->dW, h->dY, (size_t)Npad * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -510,7 +475,7 @@ gogp_status absorb(gogp_handle* h) {
     nvtxRangePop();
     ++h->launches;
     CK(cudaEventRecord(h->ev[3], s));
-    gogp_status st = ensure_pin(h, 8);
+    st = ensure_pin(h, 8);
     if (st != GOGP_OK) return st;
     CK(cudaMemcpyAsync(h->hPin, h->dRed, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->hPin + 6, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -555,6 +520,51 @@ gogp_status absorb(gogp_handle* h) {
         }
     }
     return GOGP_OK;
+}
+
+// absorb (gp/gp.go:89-239): build K, factor, alpha; then LML (gp/gp.go:244-253).
+gogp_status absorb(gogp_handle* h) {
+    h->factored = false;
+    h->have_kinv = false;
+    for (double& m : h->phase_ms) m = 0.0;
+    if (!h->has_data) {  // gp.X was never assigned: len(gp.X) == 0, the prior (gp/gp.go:101-104)
+        h->N = 0;
+        h->Npad = 0;
+        h->has_data = true;
+    }
+    if (h->N == 0) {
+        h->lml = 0.0;
+        h->factored = true;
+        h->have_lml = true;
+        return GOGP_OK;
+    }
+    const int64_t N = h->N, Npad = h->Npad;
+    cudaStream_t s = h->stream;
+    DevProgram prog;
+    h->simil.bind(h->theta_s.data(), &prog);
+
+    CK(cudaMemsetAsync(h->dInfo, 0, sizeof(int), s));
+    CK(cudaEventRecord(h->ev[0], s));
+    nvtxRangePushA("gogp:build");
+    launch_cov_build(prog, h->dXt, N, Npad, h->ndim, h->noise_var, h->dA, s);
+    nvtxRangePop();
+    ++h->launches;
+    CK(cudaEventRecord(h->ev[1], s));
+
+    CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
+    Blocked<CudaBackend> bl{be, h->dA, Npad, h->dWinv, rl_max(), cols_max()};
+    // per-launch accounting needs launches that do not overlap: profile on one stream
+    la_blocks(bl.la_nb);
+    if (!h->prof.on) {
+        for (auto& l : h->la) l.pending = l.below_pending = false;
+        be.la = h->la;
+    }
+    nvtxRangePushA("gogp:potrf");
+    bl.potrf_la(0, Npad, 0);
+    nvtxRangePop();
+    CK(cudaEventRecord(h->ev[2], s));
+
+    return finish_solve(h);
 }
 
 }  // namespace
@@ -958,6 +968,118 @@ gogp_status gogp_optimize(gogp_handle* h, const gogp_opt_settings* st, double* l
     // evaluation was there (the memo answers), one more factorisation if the line search ended on a rejected trial
     double lml_at = 0.0;
     return gogp_observe(h, x.data(), 0, nullptr, nullptr, 0, &lml_at);
+}
+
+// the expanding window of tutorial.Evaluate (tutorial/tutorial.go:91-179) grows by one
+// observation per step.  With the hyper-parameters UNCHANGED, the factor of the first N observations is the leading
+// block of the factor of N + m, so only the block rows from the last (possibly partial) tile on are new:
+//     L21 = K21 L11^-T   (blocked solve, (N + m - r0) x r0),   L22 L22^T = K22 - L21 L21^T,   r0 = 128 floor(N / 128)
+// O(N^2 (m + 128)) flops instead of O((N + m)^3); alpha and the LML are then re-solved (O(N^2)).
+gogp_status gogp_extend(gogp_handle* h, const double* Xnew, const double* Ynew, int64_t m, double* lml) {
+    if (!h || m < 0 || !lml) return GOGP_BAD_ARGUMENT;
+    if (m > 0 && (!Xnew || !Ynew)) return fail(h, GOGP_BAD_ARGUMENT, "X and Y of the new observations must be given");
+    CK(cudaSetDevice(h->dev));
+    if (!h->factored || !h->have_lml || h->with_obs)
+        return fail(h, GOGP_NOT_READY, "gogp_extend needs observations absorbed in the hyper-parameters-only form");
+    if (m == 0) {
+        *lml = h->lml;
+        return GOGP_OK;
+    }
+    const int64_t N0 = h->N, Npad0 = h->Npad, N1 = N0 + m, Npad1 = pad_tile(N1);
+    const int D = h->ndim;
+    cudaStream_t s = h->stream;
+    if (N0 == 0) {  // nothing to extend: the new observations are the data
+        gogp_status st = upload_data(h, Xnew, Ynew, m);
+        if (st != GOGP_OK) return st;
+        st = absorb(h);
+        if (st == GOGP_OK || st == GOGP_ILL_CONDITIONED) *lml = h->lml;
+        return st;
+    }
+    // ---- storage: the vectors grow with slack; the matrix is re-laid out when the padded size changes (its leading
+    // dimension IS the padded size) -- an O(N^2) copy per 128 appended observations
+    double *nXraw = nullptr, *nXt = nullptr, *nY = nullptr, *nA = nullptr, *nWinv = nullptr;
+    const bool regrow = Npad1 > h->cap;
+    const int64_t cap1 = regrow ? pad_tile(Npad1 + Npad1 / 4) : h->cap;
+    if (regrow) {
+        const size_t v = (size_t)cap1 * sizeof(double);
+        CK(cudaMalloc(&nXraw, v * D));
+        CK(cudaMalloc(&nXt, v * D));
+        CK(cudaMalloc(&nY, v));
+        CK(cudaMalloc(&nWinv, v * TILE));
+        CK(cudaMemcpyAsync(nXraw, h->dXraw, (size_t)N0 * D * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(nY, h->dY, (size_t)Npad0 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(nWinv, h->dWinv, (size_t)Npad0 * TILE * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+    if (Npad1 != Npad0 || regrow) {
+        CK(cudaMalloc(&nA, (size_t)cap1 * cap1 * sizeof(double)));
+        CK(cudaMemcpy2DAsync(nA, (size_t)Npad1 * sizeof(double), h->dA, (size_t)Npad0 * sizeof(double),
+                             (size_t)Npad0 * sizeof(double), (size_t)Npad0, cudaMemcpyDeviceToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    if (regrow) {
+        free_dev(h->dXraw); free_dev(h->dXt); free_dev(h->dY); free_dev(h->dWinv);
+        free_dev(h->dAlpha); free_dev(h->dW); free_dev(h->dZ); free_dev(h->dGx);
+        free_dev(h->dB); free_dev(h->dDg); free_dev(h->dPartial);
+        h->cap_grad = 0;
+        h->dXraw = nXraw; h->dXt = nXt; h->dY = nY; h->dWinv = nWinv;
+        const size_t v = (size_t)cap1 * sizeof(double);
+        CK(cudaMalloc(&h->dAlpha, v));
+        CK(cudaMalloc(&h->dW, v));
+        CK(cudaMalloc(&h->dZ, v));
+        CK(cudaMalloc(&h->dGx, v * D));
+        if (cap1 / TILE + 1 > h->syncCap) {
+            if (h->dSync) cudaFree(h->dSync);
+            h->dSync = nullptr;
+            h->syncCap = 0;
+            CK(cudaMalloc(&h->dSync, (size_t)(cap1 / TILE + 1) * sizeof(unsigned)));
+            h->syncCap = cap1 / TILE + 1;
+        }
+        h->cap = cap1;
+    }
+    if (nA) {
+        free_dev(h->dA);
+        h->dA = nA;
+    }
+    {
+        gogp_status st = ensure_scratch(h, Npad1);
+        if (st != GOGP_OK) return st;
+    }
+    // ---- the new observations
+    CK(cudaMemcpyAsync(h->dXraw + N0 * D, Xnew, (size_t)m * D * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->dY + N0, 0, (size_t)(Npad1 - N0) * sizeof(double), s));
+    CK(cudaMemcpyAsync(h->dY + N0, Ynew, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+    launch_transpose_x(h->dXraw, h->dXt, N1, Npad1, D, s);
+    ++h->launches;
+    h->N = N1;
+    h->Npad = Npad1;
+    h->factored = false;
+    h->have_kinv = false;
+    h->memo_valid = false;
+    for (double& t : h->phase_ms) t = 0.0;
+    // ---- block rows r0 .. Npad1 of K, then of L
+    const int64_t r0 = (N0 / TILE) * TILE, m2 = Npad1 - r0;
+    DevProgram prog;
+    h->simil.bind(h->theta_s.data(), &prog);
+    CK(cudaMemsetAsync(h->dInfo, 0, sizeof(int), s));
+    CK(cudaEventRecord(h->ev[0], s));
+    double* B = h->dA + r0 * Npad1;  // rows r0.., columns 0..r0
+    if (r0 > 0)
+        launch_cov_rect_block(prog, h->dXt + r0, Npad1, N1 - r0, (int)(m2 / TILE), h->dXt, Npad1, r0, (int)(r0 / TILE), D, B,
+                              Npad1, s);
+    launch_cov_sym_block(prog, h->dXt + r0, Npad1, N1 - r0, (int)(m2 / TILE), D, h->noise_var, B + r0, Npad1, s);
+    h->launches += 2;
+    CK(cudaEventRecord(h->ev[1], s));
+    CudaBackend be{s, h->dInfo, &h->launches, &h->prof, h->dScr, h->scrRows};
+    Blocked<CudaBackend> bl{be, h->dA, Npad1, h->dWinv, rl_max(), cols_max()};
+    if (r0 > 0) {
+        bl.trsm(B, Npad1, m2, 0, r0);
+        be.gemm(B + r0, Npad1, B, Npad1, B, Npad1, m2, m2, r0, -1.0, 1.0, GEMM_LOWER, nullptr);
+    }
+    bl.potrf(r0, m2);
+    CK(cudaEventRecord(h->ev[2], s));
+    gogp_status st = finish_solve(h);
+    if (st == GOGP_OK || st == GOGP_ILL_CONDITIONED) *lml = h->lml;
+    return st;
 }
 
 gogp_status gogp_get_alpha(gogp_handle* h, double* alpha, int64_t N) {

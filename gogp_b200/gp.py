@@ -136,6 +136,29 @@ class GP:
             return GoGPError(st, self._err(st))
         return None
 
+    # -- tutorial/tutorial.go:91-179, the window that grows ---------
+    def Extend(self, x, y):
+        """Append observations to the absorbed ones at UNCHANGED hyper-parameters: the factor is extended
+        (O(N^2) per appended point) instead of recomputed.  Returns None or a GoGPError, like Absorb; the result equals
+        Absorb on the concatenated data."""
+        h = self._handle()
+        Xn = _flat(x, self.NDim)
+        Yn = _flat(y, 0)
+        m = len(Yn)
+        if Xn.size != m * self.NDim:
+            return GoGPError(_lib.BAD_ARGUMENT, "len(x) != len(y)")
+        out = C.c_double(0.0)
+        st = _lib.lib().gogp_extend(h, _lib.dptr(Xn), _lib.dptr(Yn), m, C.byref(out))
+        if st != _lib.OK and st != _lib.ILL_CONDITIONED:
+            return GoGPError(st, self._err(st))
+        if m:
+            X0 = _flat(self.X, self.NDim).reshape(-1, self.NDim)
+            self.X = np.concatenate([X0, Xn.reshape(m, self.NDim)])
+            self.Y = np.concatenate([_flat(self.Y, 0), Yn])
+        self._n += m
+        self._with_obs = False
+        return None if st == _lib.OK else GoGPError(st, self._err(st))
+
     # -- gp/gp.go:244-253 ------------------------------------------------------------
     def LML(self):
         out = C.c_double(0.0)

@@ -132,6 +132,13 @@ gogp_status gogp_gradient(gogp_handle* h, double* grad, int64_t len);
 gogp_status gogp_absorb(gogp_handle* h, const double* theta_simil, const double* theta_noise,
                         const double* X, const double* Y, int64_t N);
 
+/* The expanding window of tutorial.Evaluate (tutorial/tutorial.go:91-179): append m
+ * observations to the absorbed ones WITH THE HYPER-PARAMETERS UNCHANGED.  The factor of the first N observations is
+ * the leading block of the new one, so only the block rows from the last (partial) 128-tile on are rebuilt and
+ * factored: O(N^2 (m + 128)) instead of O((N + m)^3); alpha and the LML follow.  Equivalent to gogp_absorb on all
+ * N + m observations (results agree to rounding); needs the hyper-parameters-only form (no with_obs). */
+gogp_status gogp_extend(gogp_handle* h, const double* Xnew, const double* Ynew, int64_t m, double* lml);
+
 /* gp.GP.LML (gp/gp.go:244-253) of the absorbed observations; 0 when N == 0. */
 gogp_status gogp_lml(gogp_handle* h, double* lml);
 

@@ -479,3 +479,93 @@ def test_ill_conditioned_is_an_error_with_a_complete_state():
     g = GP(NDim=1, Simil=k.Normal, Noise=k.ConstantNoise(np.sqrt(1e-9)), ThetaSimil=[1.0])
     assert g.Absorb(X, y) is None          # suspicious diagonal (stage 1), cleared by the estimate (stage 2)
     g.close()
+
+
+# ---- the window that grows (tutorial/tutorial.go:91-179) -------------------------
+@pytest.mark.parametrize("name,N0,m", [("c5_matern4", 0, 5), ("c5_matern4", 1, 1), ("c5_matern4", 100, 29),
+                                       ("c5_matern4", 127, 1), ("c5_matern4", 128, 1), ("hyperpriors", 300, 200),
+                                       ("c3_ard3", 1000, 300)])
+def test_extend_equals_absorb(name, N0, m):
+    """gogp_extend: the factor of N0 observations extended by m at unchanged hyper-parameters is the factor of
+    N0 + m -- LML, alpha and the predictions agree with a fresh Absorb of everything, and with the oracle."""
+    X, y, logt = cases.synth(name, N0 + m, seed=17)
+    theta = np.exp(logt)
+    nts = cases.CASES[name][1].NTheta()
+    g = cases.make_device_gp(name)
+    g.ThetaSimil, g.ThetaNoise = list(theta[:nts]), list(theta[nts:])
+    assert g.Absorb(X[:N0], y[:N0]) is None
+    assert g.Extend(X[N0:], y[N0:]) is None
+    ref = cases.make_device_gp(name)
+    ref.ThetaSimil, ref.ThetaNoise = list(theta[:nts]), list(theta[nts:])
+    assert ref.Absorb(X, y) is None
+    N = N0 + m
+    assert abs(g.LML() - ref.LML()) <= 1e-11 * max(abs(ref.LML()), N)
+    a, b = g.Alpha(), ref.Alpha()
+    assert len(a) == N and np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b)))
+    Z = X[:7] + 0.01
+    mu, sg, err = g.Produce(Z)
+    mu2, sg2, err2 = ref.Produce(Z)
+    assert err is None and err2 is None
+    assert np.max(np.abs(mu - mu2)) <= 1e-9 * max(1.0, np.max(np.abs(mu2))) and np.max(np.abs(sg ** 2 - sg2 ** 2)) <= 1e-9
+    og = cases.make_oracle_gp(name)
+    og.ThetaSimil, og.ThetaNoise = theta[:nts].copy(), theta[nts:].copy()
+    og.absorb(X, y)
+    assert abs(g.LML() - og.lml()) <= LML_TOL * max(abs(og.lml()), N)
+    # the extended handle goes on as a GP: Observe at a new point refactors everything
+    og2 = cases.make_oracle_gp(name)
+    og2.X, og2.Y = X, y
+    assert abs(g.Observe(logt.copy() + 0.05) - og2.observe(logt.copy() + 0.05)) <= LML_TOL * N
+    g.close()
+    ref.close()
+
+
+def test_extend_point_by_point_across_tile_boundaries():
+    name = "barebones"
+    X, y, logt = cases.synth(name, 270, seed=19)
+    theta = np.exp(logt)
+    nts = cases.CASES[name][1].NTheta()
+    g = cases.make_device_gp(name)
+    g.ThetaSimil, g.ThetaNoise = list(theta[:nts]), list(theta[nts:])
+    assert g.Absorb(X[:120], y[:120]) is None
+    og = cases.make_oracle_gp(name)
+    og.ThetaSimil, og.ThetaNoise = theta[:nts].copy(), theta[nts:].copy()
+    for end in range(120, 270):
+        assert g.Extend(X[end:end + 1], y[end:end + 1]) is None
+        if end in (126, 127, 128, 200, 255, 256, 269):
+            og.absorb(X[:end + 1], y[:end + 1])
+            assert abs(g.LML() - og.lml()) <= LML_TOL * max(abs(og.lml()), end + 1), end
+    g.close()
+
+
+def test_tutorial_evaluate_driver():
+    """gogp_b200.tutorial.Evaluate (tutorial/tutorial.go:56-230) on the shipped barebones data: with the
+    hyper-parameters held (jitter 0, no optimisation) the window grows by GP.Extend and must print what a loop of
+    fresh fits prints; with the reference's defaults (jitter, L-BFGS) the rows have the reference's columns."""
+    import io
+    from gogp_b200 import tutorial
+    name = "barebones"
+    text = open(cases.GOLDEN + "/%s.csv" % name).read()
+    X, Y = tutorial.load(text)
+    mean, std = tutorial.mean_std(Y)
+    Yn = (Y - mean) / std
+    g = cases.make_device_gp(name)
+    P = g.Simil.NTheta() + g.Noise.NTheta()
+    out = io.StringIO()
+    rows = tutorial.Evaluate(g, g, np.zeros(P), text, out, jitter=0.0, optimise=False)
+    assert len(rows) == len(X) and len(out.getvalue().splitlines()) == len(X)
+    ref = cases.make_device_gp(name)
+    ref.ThetaSimil, ref.ThetaNoise = [1.0] * ref.Simil.NTheta(), [1.0] * ref.Noise.NTheta()
+    for end in range(len(X)):
+        assert ref.Absorb(X[:end], Yn[:end]) is None
+        mu, sigma, err = ref.Produce(X[end:end + 1])
+        want = list(X[end]) + [Y[end], mu[0] * std + mean, sigma[0] * std, ref.LML(), ref.LML()] + [1.0] * P
+        assert np.max(np.abs(np.array(rows[end]) - np.array(want))) <= 1e-9 * max(1.0, np.max(np.abs(want))), end
+    # the reference's defaults: jittered start, L-BFGS inside the library; 1 + 5 + P columns, "%f" formatted
+    out2 = io.StringIO()
+    rows2 = tutorial.Evaluate(g, g, np.zeros(P), text, out2, iters=20, rng=np.random.default_rng(3))
+    lines = out2.getvalue().splitlines()
+    assert len(lines) == len(X) and all(len(l.split(",")) == 1 + 5 + P for l in lines)
+    assert all(np.isfinite(r).all() for r in rows2)
+    assert all(r[5] >= r[4] - 1e-9 for r in rows2[2:])   # optimisation does not lower the LML (lml >= lml0)
+    g.close()
+    ref.close()

@@ -168,3 +168,14 @@ def test_grid_has_no_cpu_fallback_either(built_lib):
     with pytest.raises(g.GoGPPanic) as e:
         g.GridGP(NDim=1, Simil=k.Normal, Noise=k.ConstantNoise(0.1), Devices=[0])
     assert e.value.status == g._lib.CUDA_ERROR
+
+
+def test_tutorial_csv_format():
+    """tutorial.load (tutorial/tutorial.go:234-272): D inputs then one output per record; a bad field is an error."""
+    from gogp_b200 import tutorial
+    X, Y = tutorial.load("0.5,1.5,2\n1,2,3.25\n")
+    assert X.shape == (2, 2) and np.array_equal(Y, [2.0, 3.25]) and X[1, 1] == 2.0
+    with pytest.raises(ValueError):
+        tutorial.load("1,x\n")
+    m, s = tutorial.mean_std([1.0, 2.0, 3.0, 4.0])
+    assert m == 2.5 and abs(s - np.std([1, 2, 3, 4], ddof=1)) < 1e-15
