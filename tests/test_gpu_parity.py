@@ -569,3 +569,47 @@ def test_tutorial_evaluate_driver():
     assert all(r[5] >= r[4] - 1e-9 for r in rows2[2:])   # optimisation does not lower the LML (lml >= lml0)
     g.close()
     ref.close()
+
+
+# ---- the largest sizes the oracle can still do on the host (SURVEY.md section 8c iii) --------------------
+@pytest.mark.parametrize("name", ["c5_matern4", "hyperpriors", "c3_ard8"])
+def test_n8192_vs_oracle(name):
+    """LML, alpha and gradient at N = 8192 (64 tiles: every level of the look-ahead factorisation, the TMA GEMM,
+    the single-launch solves, the specialised and the multi-term trace) against the oracle's `fast` mode."""
+    N = 8192
+    X, y, logt = cases.synth(name, N, seed=41)
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    lml = dg.Observe(logt.copy())
+    grad = dg.Gradient()
+    ref = og.observe(logt.copy())
+    gref = og.gradient("fast")
+    assert abs(lml - ref) <= LML_TOL * max(abs(ref), N), (lml, ref)
+    assert _grad_err(grad, gref) <= GRAD_TOL, (grad, gref)
+    a = dg.Alpha()
+    assert np.max(np.abs(a - og.Alpha)) <= GRAD_TOL * max(1.0, np.max(np.abs(og.Alpha)))
+    dg.close()
+
+
+@pytest.mark.parametrize("name,N", [("warpedtime", 2048), ("c3_ard3", 1024)])
+def test_with_obs_large_vs_oracle(name, N):
+    """The tutorial anynoise / warpedtime layout, Observe([log theta | X | Y]) + Gradient with the inputs' and
+    outputs' gradient, beyond toy sizes (the reference needs N D dense N x N matrices for the same numbers)."""
+    ndim = cases.CASES[name][0]
+    X, y, logt = cases.synth(name, N, seed=43)
+    x = np.concatenate([logt, X.reshape(-1), y])
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    lml = dg.Observe(x.copy())
+    grad = dg.Gradient()
+    ref = og.observe(x.copy())
+    gref = og.gradient("fast")
+    assert len(grad) == len(logt) + N * (ndim + 1)
+    assert abs(lml - ref) <= LML_TOL * max(abs(ref), N)
+    P = len(logt)
+    assert _grad_err(grad[:P], gref[:P]) <= GRAD_TOL
+    assert _grad_err(grad[P:P + N * ndim], gref[P:P + N * ndim]) <= GRAD_TOL
+    assert _grad_err(grad[P + N * ndim:], gref[P + N * ndim:]) <= GRAD_TOL
+    dg.close()
