@@ -202,6 +202,29 @@ func (gp *GP) Absorb(x [][]float64, y []float64) error {
 	return nil
 }
 
+// Extend appends observations to the absorbed ones at unchanged hyperparameters
+// (the growing window of tutorial.Evaluate, tutorial/tutorial.go:91-179): the
+// Cholesky factor is extended, O(N^2) per appended point, instead of recomputed.
+// Equivalent to Absorb on the concatenated data.
+func (gp *GP) Extend(x [][]float64, y []float64) error {
+	h, err := gp.handle()
+	if err != nil {
+		return err
+	}
+	xf := flatten(x, gp.NDim)
+	if len(xf) != len(y)*gp.NDim {
+		return errors.New("gp: len(x) != len(y) (or a row of x is not NDim long)")
+	}
+	var lml C.double
+	if st := C.gogp_extend(h, dptr(xf), dptr(y), C.int64_t(len(y)), &lml); st != C.GOGP_OK {
+		return gp.fail(st)
+	}
+	gp.X = append(gp.X, x...)
+	gp.Y = append(gp.Y, y...)
+	gp.n += len(y)
+	return nil
+}
+
 // LML is the log marginal likelihood of the absorbed observations (gp/gp.go:244-253).
 func (gp *GP) LML() float64 {
 	var out C.double

@@ -19,6 +19,33 @@ import numpy as np
 ALG, ITERS, MINOPT, THRESHOLD, RATE = "lbfgs", 1000, 0, 1e-6, 0.01
 
 
+class HyperPriors:
+    """The Priors of tutorial/hyperpriors (tutorial/hyperpriors/model/model.go:10-40) restated for gp.Model: Normal log-densities on the log
+    hyper-parameters (c1, c2, l1, l2, p, s); c2's mean depends on c1."""
+
+    @staticmethod
+    def _logp(mu, sigma, x):
+        z = (x - mu) / sigma
+        return -0.5 * z * z - math.log(sigma) - 0.5 * math.log(2 * math.pi)
+
+    def Observe(self, x):
+        self.x = np.array(x, dtype=np.float64)
+        c1, c2, l1, l2, p, s = self.x
+        return (self._logp(-1, 1, c1) + self._logp(c1 - math.log(2), 1, c2) + self._logp(0, 2, l1) +
+                self._logp(0, 2, l2) + self._logp(0, 1, p) + self._logp(0, 1, s))
+
+    def Gradient(self):
+        c1, c2, l1, l2, p, s = self.x
+        d2 = c2 - (c1 - math.log(2))
+        return np.array([-(c1 + 1) + d2, -d2, -l1 / 4, -l2 / 4, -p, -s])
+
+    def sample(self, rng):
+        c1 = -1 + rng.standard_normal()
+        return np.array([c1, c1 - math.log(2) + rng.standard_normal(), 2 * rng.standard_normal(),
+                         2 * rng.standard_normal(), rng.standard_normal(), rng.standard_normal()])
+
+
+
 def load(rdr):
     """tutorial.go:234-272: every record is D inputs followed by one output."""
     if isinstance(rdr, (str, bytes)):

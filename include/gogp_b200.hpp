@@ -146,6 +146,22 @@ public:
         return wrap(gogp_absorb(h_, ThetaSimil.data(), ThetaNoise.data(), xf.data(), y.data(), n_));
     }
 
+    // the growing window of tutorial.Evaluate (tutorial/tutorial.go:91-179) at unchanged hyper-parameters: the factor
+    // is extended instead of recomputed; equivalent to Absorb on the concatenated data
+    Error Extend(const std::vector<std::vector<double>>& x, const std::vector<double>& y) {
+        Error e = handle();
+        if (!e.ok()) return e;
+        std::vector<double> xf = flatten(x);
+        if (xf.size() != y.size() * (size_t)NDim) return bad("len(x) != len(y) (or a row of x is not NDim long)");
+        double lml = 0.0;
+        e = wrap(gogp_extend(h_, xf.data(), y.data(), (int64_t)y.size(), &lml));
+        if (!e.ok()) return e;
+        X.insert(X.end(), x.begin(), x.end());
+        Y.insert(Y.end(), y.begin(), y.end());
+        n_ += (int64_t)y.size();
+        return e;
+    }
+
     // gp/gp.go:35-36, 255-257: the exported results a user may store, and "Produce works on stored results"
     std::vector<double> Alpha() {
         std::vector<double> a((size_t)n_, 0.0);

@@ -85,6 +85,17 @@ int main(int argc, char** argv) {
         CHECK(std::fabs(mu2[0] - mu[0]) < 1e-12 && std::fabs(sigma2[1] - sigma[1]) < 1e-12);
         e = r.Restore({1.0}, {}, {{0}, {1}}, alpha, {1.0});
         CHECK(!e.ok() && e.status == GOGP_BAD_ARGUMENT);
+        // the growing window: Absorb one point, Extend by the other == Absorb both
+        GP w(1, Normal, ConstantNoise(0.1));
+        w.ThetaSimil = {1.0};
+        e = w.Absorb({{0}}, {1});
+        CHECK(e.ok());
+        e = w.Extend({{1}}, {-1});
+        CHECK(e.ok());
+        CHECK(std::fabs(w.LML() - g.LML()) < 1e-12);
+        std::vector<double> mu3, sigma3;
+        e = w.Produce({{-2.}, {3.}}, mu3, sigma3);
+        CHECK(e.ok() && std::fabs(mu3[0] - mu[0]) < 1e-12 && std::fabs(sigma3[0] - sigma[0]) < 1e-12);
     }
     std::printf(fails ? "FAILED %d\n" : "all ok\n", fails);
     return fails ? 1 : 0;

@@ -112,3 +112,39 @@ def test_bad_start_is_reported():
         dg.Optimize(np.zeros(5), alg="adam")
     with pytest.raises(KeyError):
         dg.Optimize(x, alg="newton")
+
+
+def test_config4_restart_lbfgs_to_the_reference_thresholds():
+    """BASELINE configs[3] in small: the hyperpriors model with the tutorial's priors (gp.Model), one restart drawn
+    from the prior, L-BFGS with the reference's ITERS = 1000 / THRESHOLD = 1e-6 (tutorial/tutorial.go:26-28) inside
+    the library at N = 4096.  The oracle cannot optimise at this size in test time, so it judges the RETURNED point:
+    same objective value (1e-9), and a gradient that has collapsed relative to the start (first-order optimality)."""
+    from gogp_b200.tutorial import HyperPriors
+    name, N = "hyperpriors", 4096
+    rng = np.random.default_rng(11)
+    x_in = 0.39269908 * np.arange(N)
+    y = 0.002 * x_in + np.sin(2 * np.pi * x_in / 8.0) + 0.1 * rng.standard_normal(N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    X = x_in[:, None]
+    dg = cases.make_device_gp(name)
+    og = cases.make_oracle_gp(name)
+    dg.X, dg.Y = X, y
+    og.X, og.Y = X, y
+    priors = HyperPriors()
+    x0 = priors.sample(np.random.default_rng(7))
+    x0[2:4] = np.clip(x0[2:4], -1.5, 1.5)
+    x = x0.copy()
+    res = dg.Optimize(x, alg="lbfgs", iters=1000, threshold=1e-6, priors=priors)
+    assert res["lml"] > res["lml0"] and res["iters"] >= 5 and res["grads"] <= res["evals"]
+
+    def oracle_objective(p):
+        v = og.observe(p.copy()) + HyperPriors().Observe(p)
+        pr = HyperPriors()
+        pr.Observe(p)
+        return v, og.gradient("fast") + pr.Gradient()
+
+    v1, g1 = oracle_objective(x)
+    v0, g0 = oracle_objective(x0)
+    assert abs(v1 - res["lml"]) <= 1e-9 * max(abs(v1), N) and abs(v0 - res["lml0"]) <= 1e-9 * max(abs(v0), N)
+    assert np.max(np.abs(g1)) <= 1e-3 * max(1.0, np.max(np.abs(g0))), (g1, g0)
+    dg.close()

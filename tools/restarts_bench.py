@@ -21,32 +21,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gogp_b200 import GP, kernel as k, restarts  # noqa: E402
-
-
-class HyperPriors:
-    """tutorial/hyperpriors/model/model.go:10-40 restated: Normal log-densities on the log
-    hyper-parameters (c1, c2, l1, l2, p, s); c2's mean depends on c1."""
-
-    @staticmethod
-    def _logp(mu, sigma, x):
-        z = (x - mu) / sigma
-        return -0.5 * z * z - math.log(sigma) - 0.5 * math.log(2 * math.pi)
-
-    def Observe(self, x):
-        self.x = np.array(x, dtype=np.float64)
-        c1, c2, l1, l2, p, s = self.x
-        return (self._logp(-1, 1, c1) + self._logp(c1 - math.log(2), 1, c2) + self._logp(0, 2, l1) +
-                self._logp(0, 2, l2) + self._logp(0, 1, p) + self._logp(0, 1, s))
-
-    def Gradient(self):
-        c1, c2, l1, l2, p, s = self.x
-        d2 = c2 - (c1 - math.log(2))
-        return np.array([-(c1 + 1) + d2, -d2, -l1 / 4, -l2 / 4, -p, -s])
-
-    def sample(self, rng):
-        c1 = -1 + rng.standard_normal()
-        return np.array([c1, c1 - math.log(2) + rng.standard_normal(), 2 * rng.standard_normal(),
-                         2 * rng.standard_normal(), rng.standard_normal(), rng.standard_normal()])
+from gogp_b200.tutorial import HyperPriors  # noqa: E402
 
 
 def synth(N, seed=0):
