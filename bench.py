@@ -335,6 +335,31 @@ def config_records(L, _lib, device):
         "produce_wall_ms": 1e3 * t_prod / reps,
         "note": "latency-bound chains at this size: N^3 flop = 1.9 ms at the DMMA peak"}
     g.close()
+    # several handles on the one GPU (multi-start restarts): one restart's tile chains overlap another's GEMMs
+    import threading
+    H, per = 3, 12
+    gs = [GP(NDim=1, Simil=k.Param(0) * k.Normal.Of(l=1), Noise=k.UniformNoise, Device=device) for _ in range(H)]
+    thetas = [[truth + 0.1 * rng.standard_normal(3) for _ in range(per + 2)] for _ in range(H)]
+
+    def work(hh, lo, hi):
+        gs[hh].X, gs[hh].Y = X, y
+        for i in range(lo, hi):
+            gs[hh].Observe(thetas[hh][i]); gs[hh].Gradient()
+
+    for hh in range(H):
+        work(hh, 0, 2)
+    ths = [threading.Thread(target=work, args=(hh, 2, per + 2)) for hh in range(H)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    out["c2_rbf_n4096"]["concurrent_handles"] = {
+        "handles": H, "evals_per_s_wall": H * per / dt,
+        "note": "independent restarts on one GPU, one handle + host thread each (SURVEY.md section 8e)"}
+    for gg in gs:
+        gg.close()
     # ---- with_obs input gradient (tutorial anynoise / warpedtime layout) at N = 4096 -------------------
     g = GP(NDim=1, Simil=k.Param(0) * k.Matern52.Of(l=1), Noise=0.01 * k.UniformNoise, Device=device)
     th = np.array([0.0, 0.0, np.log(1.0)])

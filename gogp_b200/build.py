@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libgogp_b200.so")
 
 CU_SOURCES = ["capi.cu", "cov.cu", "dgemm.cu", "dgemm_tma.cu", "leaf.cu", "grid.cu"]
 CC_SOURCES = ["program.cc"]
-HEADERS = ["program.h", "kexpr.cuh", "kernels.h", "blocked.hpp", "grid.hpp", "optimize.hpp", "leaf_kernels.cuh", "cov_kernels.cuh", "dgemm_kernels.cuh", "dgemm_tma_kernel.cuh", os.path.join("..", "..", "include", "gogp_b200.h")]
+HEADERS = ["program.h", "kexpr.cuh", "kernels.h", "blocked.hpp", "grid.hpp", "peer_bcast.hpp", "optimize.hpp", "leaf_kernels.cuh", "cov_kernels.cuh", "dgemm_kernels.cuh", "dgemm_tma_kernel.cuh", os.path.join("..", "..", "include", "gogp_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

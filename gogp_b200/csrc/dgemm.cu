@@ -103,8 +103,9 @@ void launch_dgemm_nt(double* C, int64_t ldc, const double* A, int64_t lda, const
     if (k <= 0) return;
     // Latency shapes: a launch of a few 128 x 128 tiles is bound by one SM's DMMA rate per tile, not by the GPU's;
     // quarter tiles with 32 x 32 warp tiles spread it over 4x the SMs (GOGP_SMALL_TILES: at most this many
-    // 128-tiles, default 36 = a quarter of the SMs; 0 switches the shapes off).
-    static int64_t small_tiles = 36;
+    // 128-tiles, default 110: 4x the CTAs still fit in about three per SM; a sweep over 36 .. 296 at N = 4096 moved the
+    // evaluation by 4 % only; 0 switches the shapes off).
+    static int64_t small_tiles = 110;
     static std::once_flag small_knob;
     std::call_once(small_knob, [] {
         const char* e = getenv("GOGP_SMALL_TILES");

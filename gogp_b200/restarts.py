@@ -52,6 +52,31 @@ def run_share(evaluate, starts, rank=0, world=1, iters=0, optimise=None):
     return lmls, thetas
 
 
+def run_share_concurrent(optimisers, starts, rank=0, world=1):
+    """run_share with several device handles on ONE GPU ("optionally 2 handles per GPU to
+    overlap one restart's panel latency with another's GEMM"): `optimisers` holds one start -> (objective, theta)
+    callable per handle; this rank's restarts are dealt round-robin to one host thread per handle.  A handle is not
+    thread-safe, distinct handles are (include/gogp_b200.h); the C calls release the interpreter lock."""
+    import threading
+    starts = np.asarray(starts, dtype=np.float64)
+    R, P = starts.shape
+    lmls = np.full(R, -np.inf)
+    thetas = np.array(starts, copy=True)
+    mine = shard(R, rank, world)
+    H = len(optimisers)
+
+    def work(hh):
+        for r in mine[hh::H]:
+            lmls[r], thetas[r] = optimisers[hh](starts[r].copy())
+
+    threads = [threading.Thread(target=work, args=(hh,)) for hh in range(H)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    return lmls, thetas
+
+
 def gather_results(lmls, thetas, rank=0, world=1, dist=None):
     """The only exchange of the sharded restarts: every rank receives every restart's
     (objective, theta), R*(P+1) doubles per rank.  Returns (lmls, thetas, best index)."""

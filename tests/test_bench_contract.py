@@ -44,7 +44,7 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 def test_committed_b200_bench_line_has_every_contract_key():
     """The last bench line measured on the B200 (profiles/): the keys the driver and the judge read."""
-    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_g1_v1.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_g1_v2.json")))
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert key in d, key
