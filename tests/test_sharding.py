@@ -72,3 +72,26 @@ def test_two_rank_gloo_matches_single_rank(tmp_path):
     ref = np.concatenate([lmls, thetas.ravel(), [best]])
     assert np.allclose(r0, ref, rtol=0, atol=1e-12)
     assert np.all(np.isfinite(lmls))
+
+
+def test_several_handles_per_gpu_deal_the_share_round_robin():
+    """run_share_concurrent: this rank's restarts are dealt to one host thread per handle; every restart is
+    optimised exactly once and lands in its own row."""
+    from gogp_b200 import restarts
+    starts = np.arange(22, dtype=np.float64).reshape(11, 2)
+    seen = [[], [], []]
+
+    def make(hh):
+        def optimise(x0):
+            seen[hh].append(int(x0[0]) // 2)
+            return float(-x0.sum()), x0 + 1.0
+        return optimise
+
+    lmls, thetas = restarts.run_share_concurrent([make(0), make(1), make(2)], starts, rank=1, world=2)
+    mine = restarts.shard(11, 1, 2)
+    assert sorted(seen[0] + seen[1] + seen[2]) == mine and seen[0] == mine[0::3] and seen[1] == mine[1::3]
+    for r in range(11):
+        if r in mine:
+            assert lmls[r] == -starts[r].sum() and np.array_equal(thetas[r], starts[r] + 1.0)
+        else:
+            assert lmls[r] == -np.inf and np.array_equal(thetas[r], starts[r])
