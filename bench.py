@@ -54,6 +54,9 @@ NOMINAL_FP64_TFLOPS = 148 * 128 * 1.965e9 / 1e12  # 64 FP64 FMA/clk/SM at clocks
 # `ncu --set full` capture profiles/r1_gemm_v3_tma_ncu_raw.csv (a number taken under the profiler is evidence
 # of traffic, never a timing): the 8192 x 8192 x 8192 C -= A B^T launch of tools/gemm_bench.py
 GEMM_NCU_TRAFFIC = {"dram_bytes": 6.328994e9 + 0.530380e9, "launch": "dgemm_tma_kernel, m=n=k=8192",
+                    "scope": "ONE 8192^3 launch of the dominant kernel under ncu (a micro-run), NOT the bench step: the "
+                             "step's 199 TMA GEMM launches have other shapes; the kernel is tensor-bound, its DRAM "
+                             "traffic (224 GB/s here) is far from the HBM roofline either way",
                     "algorithmic_bytes": 4 * 8192 * 8192 * 8, "duration_ms_under_ncu": 30.58,
                     "dmma_pipe_pct_of_active": 97.87, "tensor_pipe_pct_of_elapsed": 94.26, "l2_hit_pct": 83.4,
                     "source": "profiles/r1_gemm_v3_tma_ncu_raw.csv"}
