@@ -78,7 +78,7 @@ NcclApi* nccl() {
 }
 const char* nccl_load_error() { return "NCCL is not available (libnccl.so.2 could not be bound; set GOGP_NCCL_LIB)"; }
 
-constexpr int kNcclMaxCtas = 0;  // default cap on the CTAs of a collective (see rank_create); 0: NCCL's choice
+constexpr int kNcclMaxCtas = 0;  // cap on the CTAs of a collective (see rank_create); 0: NCCL's choice, the measured best
 
 __global__ void int_to_double_kernel(const int* src, double* dst) { *dst = (double)*src; }
 
@@ -367,10 +367,11 @@ gogp_status rank_create(GridRank& r, int ndim, const gogp_op* simil, int n_simil
         ncclUniqueId uid;
         static_assert(sizeof(uid) == GOGP_GRID_ID_BYTES, "ncclUniqueId is 128 bytes");
         std::memcpy(&uid, id, sizeof(uid));
-        // The collectives share the GPU with the DMMA GEMMs of the side queue: every CTA NCCL holds (mostly spinning
-        // on a peer whose panel is not ready yet) is an SM the trailing update cannot use.  The panels are tens of
-        // MB per step against tens of ms of GEMMs, so a few CTAs of copy bandwidth are plenty: cap them
-        // (GOGP_NCCL_MAX_CTAS, 0 = NCCL's own choice).
+        // The collectives share the GPU with the DMMA GEMMs of the side queue: every CTA NCCL holds is an SM the trailing
+        // update cannot use (a 197 KB GEMM CTA shares its SM with nobody), but fewer CTAs make a slower broadcast on the
+        // block-column chain.  Measured on 4 GPUs at N = 65536, maxCTAs = 1 / 2 / 4 / 8 / NCCL's choice: 3477 / 2588 /
+        // 2371 / 2304 / 2310 ms per evaluation -- so the default leaves the choice to NCCL (GOGP_NCCL_MAX_CTAS = 0); the
+        // way to get the SMs back is the copy-engine broadcast below, not a cap.
         static const int max_ctas = getenv("GOGP_NCCL_MAX_CTAS") ? atoi(getenv("GOGP_NCCL_MAX_CTAS")) : kNcclMaxCtas;
         if (max_ctas > 0 && api->CommInitRankConfig) {
             ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
