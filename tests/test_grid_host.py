@@ -94,6 +94,20 @@ def test_shapes_and_kernels(grid, name, N, NB, Pr, Pc):
     assert np.max(np.abs(grad - gref)) <= 1e-7 * max(1.0, np.max(np.abs(gref)))
 
 
+@pytest.mark.parametrize("Pr,Pc,N,NB", [(8, 1, 1100, 128), (1, 4, 1100, 128), (4, 1, 900, 128), (3, 3, 1300, 128),
+                                         (2, 2, 1100, 384), (4, 2, 2100, 256)])
+def test_more_grid_shapes(grid, Pr, Pc, N, NB):
+    """Grids taller, wider and odder than the shipped 2 x 1 / 2 x 2 / 4 x 2, block counts that do not divide evenly,
+    blocks of three tiles: LML and gradient against the oracle."""
+    name = "barebones"
+    rc, lml, grad, alpha, stats, (X, y, logt) = _run(grid, name, N, NB, Pr, Pc, seed=9)
+    assert rc == 0
+    ref, gref, aref = _oracle(name, X, y, logt)
+    assert abs(lml - ref) <= 1e-9 * max(abs(ref), N)
+    assert np.max(np.abs(alpha - aref)) <= 1e-7 * max(1.0, np.max(np.abs(aref)))
+    assert np.max(np.abs(grad - gref)) <= 1e-7 * max(1.0, np.max(np.abs(gref)))
+
+
 def test_the_mask_skips_the_upper_half_and_flops_stay_at_n_cubed(grid):
     """GEMM tiles actually computed over the whole grid ~ (N/128)^3 tile steps per LML + gradient evaluation:
     the masked launches must not compute (or write) blocks above the global diagonal."""
