@@ -206,6 +206,14 @@ def lbfgs_ascent(value_grad, x0, iters, threshold, history=15):
     return x, f, it
 
 
+def parse_events(spec):
+    """tutorial/events/main.go:17-63: the -events flag, "from:to:discount,..." (e.g. "1.:2.5:0.3,3:6:0.5") -> rows for
+    kernel.Events / gogp_set_events.  A malformed number raises, as the reference panics."""
+    if not spec:
+        return []
+    return [tuple(float(v) for v in event.split(":")) for event in spec.split(",")]
+
+
 def load(rdr):
     """tutorial.go:234-272: every record is D inputs followed by one output."""
     if isinstance(rdr, (str, bytes)):

@@ -93,3 +93,12 @@ def test_evaluate_in_optinp_mode(name, model, priors):
         gx = np.asarray(g.X).reshape(-1)
         assert gx[0] == X[0, 0] and gx[-1] == X[12, 0] and np.allclose(np.asarray(g.Y), (Y[:13] - mean) / std)
         assert not np.allclose(gx[1:-1], X[1:12, 0])
+
+
+def test_events_flag_format():
+    assert T.parse_events("1.:2.5:0.3,3:6:0.5") == [(1.0, 2.5, 0.3), (3.0, 6.0, 0.5)] and T.parse_events("") == []
+    with pytest.raises(ValueError):
+        T.parse_events("1:x:0.3")
+    from gogp_b200 import kernel as k
+    e = k.Param(0) * k.Matern52.Of(l=1) * k.Events(T.parse_events("1.:2.5:0.3,3:6:0.5"))
+    assert e.NTheta() == 2 and len(e.events) == 2
